@@ -1,0 +1,124 @@
+/*
+ * repsurf_b200.h — C-ABI of librepsurf_b200.so (sm_100a kernels for the RepSurf-U hot path).
+ *
+ * This is the drop-in boundary.  Each entry replaces one `extern "C" *_cuda_launcher` of the
+ * reference's pointops extension (declared in its *_cuda_kernel.h files) with the same argument
+ * order and meaning, plus:
+ *   - an explicit cudaStream_t on EVERY entry (the reference launches most kernels on the legacy
+ *     default stream; only ballquery_fast / knnquery / knnquery_heap take a stream), and
+ *   - an int status return: 0 on success, otherwise a cudaError_t value with a message available
+ *     from rsb_last_error() (the reference's `_fast` launchers print and exit(-1), the others do
+ *     not check at all).
+ * All pointers are DEVICE pointers to contiguous fp32 / int32 arrays on the current device.
+ * Ownership is the reference's: the caller allocates every output and scratch buffer; kernels
+ * write in place; nothing is retained after return; all work is asynchronous on `stream`.
+ * Thread-safety: entries are re-entrant; rsb_last_error() is per host thread.
+ *
+ * Paths below are relative to the reference repository root; cls/po = classification/modules/pointops,
+ * seg/po = segmentation/modules/pointops.
+ */
+#ifndef REPSURF_B200_H
+#define REPSURF_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int rsb_abi_version(void);
+const char *rsb_last_error(void);
+unsigned long long rsb_launch_count(void);   /* kernels launched by this library since the last reset */
+void rsb_reset_launch_count(void);
+
+/* ------------------------------------------------------------------ dense layout (classification) */
+
+/* replaces furthestsampling_cuda_launcher(b,n,m,dataset,temp,idxs)      cls/po/src/sampling/sampling_cuda_kernel.h:19
+ * xyz [b,n,3]; temp [b,n] scratch or NULL (no need to pre-fill; final running minima are written back
+ * when given); idx [b,m] int32, idx[:,0] = 0.  new_xyz: optional [b,m,3] fused gather of the sampled
+ * coordinates (NULL to skip) — replaces the separate gathering call of cls/modules/repsurface_utils.py:30. */
+int rsb_furthestsampling_dense(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz,
+                               cudaStream_t stream);
+
+/* replaces gathering_forward_cuda_launcher / gathering_backward_cuda_launcher   cls/po/src/sampling/sampling_cuda_kernel.h:17-18
+ * points [b,c,n], idx [b,m] -> out [b,c,m]; backward accumulates (atomicAdd) into a caller-zeroed grad_points [b,c,n]. */
+int rsb_gathering_forward(int b, int c, int n, int m, const float *points, const int *idx, float *out,
+                          cudaStream_t stream);
+int rsb_gathering_backward(int b, int c, int n, int m, const float *grad_out, const int *idx, float *grad_points,
+                           cudaStream_t stream);
+
+/* replaces ballquery_cuda_launcher_fast(b,n,m,radius,nsample,new_xyz,xyz,idx,stream)   cls/po/src/ballquery/ballquery_cuda_kernel.h:17
+ * idx [b,m,nsample]: first nsample indices (ascending) with d2 < radius^2, padded with the first hit, zeros if none.
+ * Unlike the reference the output need not be pre-zeroed. */
+int rsb_ballquery(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx,
+                  cudaStream_t stream);
+
+/* replaces knnquery_cuda_launcher(b,n,m,nsample,xyz,new_xyz,idx,dist2,stream)          cls/po/src/knnquery/knnquery_cuda_kernel.h:15
+ * idx [b,m,nsample] sorted by (d2, index); dist2 [b,m,nsample] or NULL.  1 <= nsample <= 200. */
+int rsb_knnquery_dense(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
+                       float *dist2, cudaStream_t stream);
+
+/* replaces knnquery_heap_cuda_launcher(...)                                            cls/po/src/knnquery_heap/knnquery_heap_cuda_kernel.h:15
+ * same shapes; heap order semantics (ascending d2, reference tie order).  1 <= nsample <= 100. */
+int rsb_knnquery_heap_dense(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
+                            float *dist2, cudaStream_t stream);
+
+/* replaces grouping_forward_cuda_launcher_fast / grouping_backward_cuda_launcher       cls/po/src/grouping/grouping_cuda_kernel.h:13-17
+ * points [b,c,n], idx [b,m,nsample] -> out [b,c,m,nsample]. */
+int rsb_grouping_forward(int b, int c, int n, int m, int nsample, const float *points, const int *idx, float *out,
+                         cudaStream_t stream);
+int rsb_grouping_backward(int b, int c, int n, int m, int nsample, const float *grad_out, const int *idx,
+                          float *grad_points, cudaStream_t stream);
+
+/* replaces grouping_int_forward_cuda_launcher_fast                                     cls/po/src/grouping_int/grouping_int_cuda_kernel.h:13 */
+int rsb_grouping_int_forward(int b, int c, int n, int m, int nsample, const long long *points, const int *idx,
+                             long long *out, cudaStream_t stream);
+
+/* replaces nearestneighbor_cuda_launcher_fast(b,n,m,unknown,known,dist2,idx)           cls/po/src/interpolation/interpolation_cuda_kernel.h:19
+ * unknown [b,n,3], known [b,m,3] -> dist2 [b,n,3] (squared), idx [b,n,3]. */
+int rsb_nearestneighbor(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                        cudaStream_t stream);
+
+/* replaces interpolation_forward_cuda_launcher_fast(b,c,m,n,...) / interpolation_backward_cuda_launcher(b,n,c,m,...)
+ *                                                                                      cls/po/src/interpolation/interpolation_cuda_kernel.h:20-22
+ * points [b,c,m], idx/weight [b,n,3] -> out [b,c,n]. */
+int rsb_interpolation_forward(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                              float *out, cudaStream_t stream);
+int rsb_interpolation_backward(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ packed layout (segmentation) */
+
+/* replaces furthestsampling_cuda_launcher(b,n,xyz,offset,new_offset,tmp,idx)           seg/po/src/sampling/sampling_cuda_kernel.h:11
+ * xyz [sum n,3]; offset/new_offset [b] int32 cumulative ends (device); n_max = largest segment length
+ * (host value, as in the reference: seg/po/functions/pointops.py:39-41); idx [sum m] GLOBAL row ids.
+ * n_max_dev: optional device scalar with the exact largest segment length; when given, n_max only has to be an
+ * upper bound (it sizes the launch) and the reference's tie rule is derived from *n_max_dev on the device, so
+ * callers whose segment sizes are produced on the GPU (sectorized FPS) need no host synchronisation. */
+int rsb_furthestsampling_packed(int b, int n_max, const int *n_max_dev, const float *xyz, const int *offset,
+                                const int *new_offset, float *tmp, int *idx, float *new_xyz, cudaStream_t stream);
+
+/* replaces knnquery_cuda_launcher(m,nsample,xyz,new_xyz,offset,new_offset,idx,dist2)   seg/po/src/knnquery/knnquery_cuda_kernel.h:11
+ * adds b (= number of clouds).  dist [m,nsample]: squared distances, or their square roots when sqrt_out != 0
+ * (fuses the torch.sqrt of seg/po/functions/pointops.py:127).  1 <= nsample <= 100. */
+int rsb_knnquery_packed(int b, int m, int nsample, const float *xyz, const float *new_xyz, const int *offset,
+                        const int *new_offset, int *idx, float *dist, int sqrt_out, cudaStream_t stream);
+
+/* replaces grouping_forward/backward_cuda_launcher(m,nsample,c,...)                    seg/po/src/grouping/grouping_cuda_kernel.h:11-12
+ * input [n,c], idx [m,nsample] -> output [m,nsample,c]. */
+int rsb_grouping_packed_forward(int m, int nsample, int c, const float *input, const int *idx, float *output,
+                                cudaStream_t stream);
+int rsb_grouping_packed_backward(int m, int nsample, int c, const float *grad_output, const int *idx,
+                                 float *grad_input, cudaStream_t stream);
+
+/* replaces interpolation_forward/backward_cuda_launcher(n,c,k,...)                     seg/po/src/interpolation/interpolation_cuda_kernel.h:11-12
+ * input [m,c], idx/weight [n,k] -> output [n,c] (accumulated onto the caller-zeroed output, like the reference). */
+int rsb_interpolation_packed_forward(int n, int c, int k, const float *input, const int *idx, const float *weight,
+                                     float *output, cudaStream_t stream);
+int rsb_interpolation_packed_backward(int n, int c, int k, const float *grad_output, const int *idx,
+                                      const float *weight, float *grad_input, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPSURF_B200_H */

@@ -1,0 +1,444 @@
+/*
+ * pointops_oracle.c — CPU restatement of the reference RepSurf `pointops` kernels.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library, and only as the checker / reported CPU baseline.  The product path
+ * (repsurf_b200/) never imports it and has no CPU fallback.
+ *
+ * Parity status: the reference ships no tests or golden vectors, so this
+ * restatement is pinned two ways instead:
+ *   (1) against the reference's own Python modules imported from /root/reference and driven
+ *       through this library (oracle/make_golden.py -> tests/golden/ npz files), and
+ *   (2) on the GPU box against the reference's own CUDA kernels compiled unmodified from
+ *       /root/reference into oracle/_ref/ (oracle/build_ref.sh, tests/test_ref_kernels_gpu.py).
+ *
+ * Every function names the reference file:line it follows.  Paths are relative to
+ * /root/reference/ ; cls/po = classification/modules/pointops, seg/po = segmentation/modules/pointops.
+ *
+ * Bit-exactness rules encoded here:
+ *   R1  squared distance: nvcc contracts `dx*dx + dy*dy + dz*dz` to
+ *       t = rn(dy*dy); t = fma(dx,dx,t); d = fma(dz,dz,t).  Built with -ffp-contract=off so that
+ *       only the explicit fmaf() calls fuse.
+ *   R2  FPS arg-max: per-thread strided scan keeps the first strict maximum, the shared-memory
+ *       tree keeps the lower slot on ties.  Simulated literally (threads + tree).
+ *   R3  ball query: ascending scan, strict d2 < r*r (r*r rounded in fp32), pad with first hit.
+ *   R4  dense kNN: stable insertion, strict <, fp32 d2 compared as double, sentinel 1e40 / idx 0.
+ *   R5  heap kNN: replace root iff d2 < root; reheap prefers the right child only if strictly
+ *       larger and stops only when root > child; heap_sort => ascending.
+ *   R6  scatter-add backward kernels use atomics in the reference => order-dependent fp32 sums;
+ *       here they are summed in index order (tests compare with a tolerance).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* R1 — identical in cls/po/src/sampling/sampling_cuda_kernel.cu:92, ballquery_cuda_kernel.cu:66,
+ * knnquery_cuda_kernel.cu:31, knnquery_heap_cuda_kernel.cu:75, interpolation_cuda_kernel.cu:151,
+ * seg/po/src/sampling/sampling_cuda_kernel.cu:52, seg/po/src/knnquery/knnquery_cuda_kernel.cu:93. */
+static inline float sqdist(float ax, float ay, float az, float bx, float by, float bz)
+{
+    float dx = ax - bx, dy = ay - by, dz = az - bz;
+    float t = dy * dy;
+    t = fmaf(dx, dx, t);
+    return fmaf(dz, dz, t);
+}
+
+/* cls/po/src/cuda_utils.h:15-18 and seg/po/src/cuda_utils.h:11-14 (same formula, libm log). */
+ORC_API int orc_opt_n_threads(int work_size)
+{
+    const int pow_2 = (int)(log((double)work_size) / log(2.0));
+    int v = 1 << pow_2;
+    if (v > 1024) v = 1024;
+    if (v < 1) v = 1;
+    return v;
+}
+
+ORC_API int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* One FPS segment, simulating `furthestsampling_cuda_kernel<BS>`:
+ *   cls/po/src/sampling/sampling_cuda_kernel.cu:59-168 (dense; first = 0, idle threads hold (-1, 0))
+ *   seg/po/src/sampling/sampling_cuda_kernel.cu:15-129 (packed; first = start_n, idle threads hold (-1, start_n))
+ * xyz/tmp are indexed with absolute row ids in [start_n, end_n); idx receives absolute row ids. */
+static void fps_segment(const float *xyz, float *tmp, int start_n, int end_n, int m, int bs,
+                        int *idx_out, float *sd, int *si)
+{
+    if (m <= 0) return;
+    int old = start_n;
+    idx_out[0] = old;
+    for (int j = 1; j < m; j++) {
+        const float x1 = xyz[old * 3 + 0], y1 = xyz[old * 3 + 1], z1 = xyz[old * 3 + 2];
+        for (int t = 0; t < bs; t++) {
+            int besti = start_n;
+            float best = -1.0f;
+            for (int k = start_n + t; k < end_n; k += bs) {
+                float d = sqdist(xyz[k * 3 + 0], xyz[k * 3 + 1], xyz[k * 3 + 2], x1, y1, z1);
+                float d2 = fminf(d, tmp[k]);
+                tmp[k] = d2;
+                besti = d2 > best ? k : besti;
+                best = d2 > best ? d2 : best;
+            }
+            sd[t] = best;
+            si[t] = besti;
+        }
+        /* shared-memory tree, strides bs/2 .. 1; __update keeps slot idx1 unless v2 > v1 */
+        for (int s = bs >> 1; s >= 1; s >>= 1) {
+            for (int t = 0; t < s; t++) {
+                float v1 = sd[t], v2 = sd[t + s];
+                int i1 = si[t], i2 = si[t + s];
+                sd[t] = fmaxf(v1, v2);
+                si[t] = v2 > v1 ? i2 : i1;
+            }
+        }
+        old = si[0];
+        idx_out[j] = old;
+    }
+}
+
+/* cls: furthestsampling_cuda_launcher, cls/po/src/sampling/sampling_cuda_kernel.cu:170-210.
+ * xyz (b,n,3), temp (b,n) pre-filled by the caller (1e10, cls/po/functions/pointops.py:45), idx (b,m). */
+ORC_API void orc_fps_dense(int b, int n, int m, const float *xyz, float *temp, int *idx)
+{
+    const int bs = orc_opt_n_threads(n);
+#pragma omp parallel
+    {
+        float *sd = (float *)malloc(sizeof(float) * bs);
+        int *si = (int *)malloc(sizeof(int) * bs);
+#pragma omp for schedule(dynamic, 1)
+        for (int i = 0; i < b; i++)
+            fps_segment(xyz + (size_t)i * n * 3, temp + (size_t)i * n, 0, n, m, bs, idx + (size_t)i * m, sd, si);
+        free(sd);
+        free(si);
+    }
+}
+
+/* seg: furthestsampling_cuda_launcher, seg/po/src/sampling/sampling_cuda_kernel.cu:131-171.
+ * Block size is chosen from n_max (the caller's max segment length, seg/po/functions/pointops.py:39-41). */
+ORC_API void orc_fps_packed(int b, int n_max, const float *xyz, const int *offset, const int *new_offset,
+                            float *tmp, int *idx)
+{
+    const int bs = orc_opt_n_threads(n_max);
+#pragma omp parallel
+    {
+        float *sd = (float *)malloc(sizeof(float) * bs);
+        int *si = (int *)malloc(sizeof(int) * bs);
+#pragma omp for schedule(dynamic, 1)
+        for (int i = 0; i < b; i++) {
+            int start_n = i ? offset[i - 1] : 0, end_n = offset[i];
+            int start_m = i ? new_offset[i - 1] : 0, end_m = new_offset[i];
+            /* the kernel writes idx[start_m] unconditionally (:39) and loops j in (start_m, end_m) */
+            int m = end_m - start_m;
+            if (m <= 0) { idx[start_m] = start_n; continue; }
+            fps_segment(xyz, tmp, start_n, end_n, m, bs, idx + start_m, sd, si);
+        }
+        free(sd);
+        free(si);
+    }
+}
+
+/* cls/po/src/sampling/sampling_cuda_kernel.cu:6-19 — out[b,c,j] = points[b,c,idx[b,j]] */
+ORC_API void orc_gather_fwd(int b, int c, int n, int m, const float *points, const int *idx, float *out)
+{
+#pragma omp parallel for collapse(2)
+    for (int i = 0; i < b; i++)
+        for (int l = 0; l < c; l++)
+            for (int j = 0; j < m; j++)
+                out[((size_t)i * c + l) * m + j] = points[((size_t)i * c + l) * n + idx[(size_t)i * m + j]];
+}
+
+/* cls/po/src/sampling/sampling_cuda_kernel.cu:23-36 — scatter-add (atomicAdd in the reference, R6) */
+ORC_API void orc_gather_bwd(int b, int c, int n, int m, const float *grad_out, const int *idx, float *grad_points)
+{
+#pragma omp parallel for collapse(2)
+    for (int i = 0; i < b; i++)
+        for (int l = 0; l < c; l++)
+            for (int j = 0; j < m; j++)
+                grad_points[((size_t)i * c + l) * n + idx[(size_t)i * m + j]] += grad_out[((size_t)i * c + l) * m + j];
+}
+
+/* cls/po/src/ballquery/ballquery_cuda_kernel.cu:47-80 (the `_fast` kernel bound at pointops_api.cpp:14).
+ * idx must be pre-zeroed by the caller (cls/po/functions/pointops.py:220). */
+ORC_API void orc_ballquery(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                           const float *xyz, int *idx)
+{
+    const float radius2 = radius * radius;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; bi++)
+        for (int p = 0; p < m; p++) {
+            const float *q = new_xyz + ((size_t)bi * m + p) * 3;
+            const float *pts = xyz + (size_t)bi * n * 3;
+            int *o = idx + ((size_t)bi * m + p) * nsample;
+            int cnt = 0;
+            for (int k = 0; k < n; ++k) {
+                float d2 = sqdist(q[0], q[1], q[2], pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]);
+                if (d2 < radius2) {
+                    if (cnt == 0)
+                        for (int l = 0; l < nsample; ++l) o[l] = k;
+                    o[cnt] = k;
+                    ++cnt;
+                    if (cnt >= nsample) break;
+                }
+            }
+        }
+}
+
+/* cls/po/src/knnquery/knnquery_cuda_kernel.cu:6-50 — stable insertion into double best[200].
+ * The reference never offsets dist2 per query (:13 vs :46), so its dist2 output is a race on
+ * discarded data; here dist2 (if non-NULL) receives each query's own row, which is what the
+ * Python wrapper would need if it used it (it does not: cls/po/functions/pointops.py:316). */
+ORC_API void orc_knn_dense(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz,
+                           int *idx, float *dist2)
+{
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; bi++)
+        for (int p = 0; p < m; p++) {
+            double best[200];
+            int besti[200];
+            const float *q = new_xyz + ((size_t)bi * m + p) * 3;
+            const float *pts = xyz + (size_t)bi * n * 3;
+            for (int i = 0; i < nsample; i++) { best[i] = 1e40; besti[i] = 0; }
+            for (int k = 0; k < n; k++) {
+                float d2 = sqdist(q[0], q[1], q[2], pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]);
+                for (int j = 0; j < nsample; j++) {
+                    if (d2 < best[j]) {
+                        for (int i = nsample - 1; i > j; i--) { best[i] = best[i - 1]; besti[i] = besti[i - 1]; }
+                        best[j] = d2;
+                        besti[j] = k;
+                        break;
+                    }
+                }
+            }
+            for (int i = 0; i < nsample; i++) {
+                idx[((size_t)bi * m + p) * nsample + i] = besti[i];
+                if (dist2) dist2[((size_t)bi * m + p) * nsample + i] = (float)best[i];
+            }
+        }
+}
+
+/* reheap / heap_sort: cls/po/src/knnquery_heap/knnquery_heap_cuda_kernel.cu:21-50,
+ * seg/po/src/knnquery/knnquery_cuda_kernel.cu:21-48 (identical code). */
+static void reheap(float *dist, int *idx, int k)
+{
+    int root = 0, child = 1;
+    while (child < k) {
+        if (child + 1 < k && dist[child + 1] > dist[child]) child++;
+        if (dist[root] > dist[child]) return;
+        float tf = dist[root]; dist[root] = dist[child]; dist[child] = tf;
+        int ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
+        root = child;
+        child = root * 2 + 1;
+    }
+}
+
+static void heap_sort(float *dist, int *idx, int k)
+{
+    for (int i = k - 1; i > 0; i--) {
+        float tf = dist[0]; dist[0] = dist[i]; dist[i] = tf;
+        int ti = idx[0]; idx[0] = idx[i]; idx[i] = ti;
+        reheap(dist, idx, i);
+    }
+}
+
+static void knn_heap_one(const float *q, const float *xyz, int start, int end, int nsample, int sentinel_idx,
+                         int *idx, float *dist2)
+{
+    float best_dist[100];
+    int best_idx[100];
+    for (int i = 0; i < nsample; i++) { best_dist[i] = 1e10f; best_idx[i] = sentinel_idx; }
+    for (int i = start; i < end; i++) {
+        float d2 = sqdist(q[0], q[1], q[2], xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2]);
+        if (d2 < best_dist[0]) {
+            best_dist[0] = d2;
+            best_idx[0] = i;
+            reheap(best_dist, best_idx, nsample);
+        }
+    }
+    heap_sort(best_dist, best_idx, nsample);
+    for (int i = 0; i < nsample; i++) { idx[i] = best_idx[i]; dist2[i] = best_dist[i]; }
+}
+
+/* cls/po/src/knnquery_heap/knnquery_heap_cuda_kernel.cu:53-89 — sentinel idx 0, local indices */
+ORC_API void orc_knn_heap_dense(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz,
+                                int *idx, float *dist2)
+{
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; bi++)
+        for (int p = 0; p < m; p++)
+            knn_heap_one(new_xyz + ((size_t)bi * m + p) * 3, xyz + (size_t)bi * n * 3, 0, n, nsample, 0,
+                         idx + ((size_t)bi * m + p) * nsample, dist2 + ((size_t)bi * m + p) * nsample);
+}
+
+/* seg/po/src/knnquery/knnquery_cuda_kernel.cu:65-108 — query's cloud by linear scan of new_offset
+ * (get_bt_idx :51-62), candidates [offset[bt-1], offset[bt]), sentinel idx = start, global indices. */
+ORC_API void orc_knn_packed(int m, int nsample, const float *xyz, const float *new_xyz, const int *offset,
+                            const int *new_offset, int *idx, float *dist2)
+{
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < m; p++) {
+        int bt = 0;
+        while (!(p < new_offset[bt])) bt++;
+        int start = bt ? offset[bt - 1] : 0, end = offset[bt];
+        knn_heap_one(new_xyz + (size_t)p * 3, xyz, start, end, nsample, start, idx + (size_t)p * nsample,
+                     dist2 + (size_t)p * nsample);
+    }
+}
+
+/* cls/po/src/grouping/grouping_cuda_kernel.cu:60-74 — out[b,c,j,s] = points[b,c,idx[b,j,s]] */
+ORC_API void orc_group_fwd(int b, int c, int n, int m, int nsample, const float *points, const int *idx, float *out)
+{
+#pragma omp parallel for collapse(2)
+    for (int i = 0; i < b; i++)
+        for (int l = 0; l < c; l++) {
+            const float *src = points + ((size_t)i * c + l) * n;
+            const int *ix = idx + (size_t)i * m * nsample;
+            float *dst = out + ((size_t)i * c + l) * m * nsample;
+            for (int j = 0; j < m * nsample; j++) dst[j] = src[ix[j]];
+        }
+}
+
+/* cls/po/src/grouping/grouping_cuda_kernel.cu:28-46 (R6) */
+ORC_API void orc_group_bwd(int b, int c, int n, int m, int nsample, const float *grad_out, const int *idx,
+                           float *grad_points)
+{
+#pragma omp parallel for collapse(2)
+    for (int i = 0; i < b; i++)
+        for (int l = 0; l < c; l++) {
+            float *dst = grad_points + ((size_t)i * c + l) * n;
+            const int *ix = idx + (size_t)i * m * nsample;
+            const float *src = grad_out + ((size_t)i * c + l) * m * nsample;
+            for (int j = 0; j < m * nsample; j++) dst[ix[j]] += src[j];
+        }
+}
+
+/* cls/po/src/grouping_int/grouping_int_cuda_kernel.cu:33-49 — int64 gather */
+ORC_API void orc_group_int_fwd(int b, int c, int n, int m, int nsample, const int64_t *points, const int *idx,
+                               int64_t *out)
+{
+    for (int i = 0; i < b; i++)
+        for (int l = 0; l < c; l++)
+            for (int j = 0; j < m * nsample; j++)
+                out[((size_t)i * c + l) * m * nsample + j] =
+                    points[((size_t)i * c + l) * n + idx[(size_t)i * m * nsample + j]];
+}
+
+/* cls/po/src/interpolation/interpolation_cuda_kernel.cu:134-176 — 3-NN, fp32 d compared as double */
+ORC_API void orc_nn3(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx)
+{
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; bi++)
+        for (int p = 0; p < n; p++) {
+            const float *u = unknown + ((size_t)bi * n + p) * 3;
+            const float *kn = known + (size_t)bi * m * 3;
+            double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+            int besti1 = 0, besti2 = 0, besti3 = 0;
+            for (int k = 0; k < m; ++k) {
+                float d = sqdist(u[0], u[1], u[2], kn[k * 3], kn[k * 3 + 1], kn[k * 3 + 2]);
+                if (d < best1) {
+                    best3 = best2; besti3 = besti2;
+                    best2 = best1; besti2 = besti1;
+                    best1 = d; besti1 = k;
+                } else if (d < best2) {
+                    best3 = best2; besti3 = besti2;
+                    best2 = d; besti2 = k;
+                } else if (d < best3) {
+                    best3 = d; besti3 = k;
+                }
+            }
+            size_t o = ((size_t)bi * n + p) * 3;
+            dist2[o] = (float)best1; dist2[o + 1] = (float)best2; dist2[o + 2] = (float)best3;
+            idx[o] = besti1; idx[o + 1] = besti2; idx[o + 2] = besti3;
+        }
+}
+
+/* cls/po/src/interpolation/interpolation_cuda_kernel.cu:181-195
+ * out[b,c,p] = w0*f[i0] + w1*f[i1] + w2*f[i2]   (nvcc contracts to fma(w2,f2,fma(w1,f1,w0*f0))) */
+ORC_API void orc_interp_fwd(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                            float *out)
+{
+#pragma omp parallel for collapse(2)
+    for (int bi = 0; bi < b; bi++)
+        for (int l = 0; l < c; l++) {
+            const float *f = points + ((size_t)bi * c + l) * m;
+            for (int p = 0; p < n; p++) {
+                const int *ix = idx + ((size_t)bi * n + p) * 3;
+                const float *w = weight + ((size_t)bi * n + p) * 3;
+                float t = w[0] * f[ix[0]];
+                t = fmaf(w[1], f[ix[1]], t);
+                out[((size_t)bi * c + l) * n + p] = fmaf(w[2], f[ix[2]], t);
+            }
+        }
+}
+
+/* cls/po/src/interpolation/interpolation_cuda_kernel.cu:90-114 (R6) */
+ORC_API void orc_interp_bwd(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                            float *grad_points)
+{
+#pragma omp parallel for collapse(2)
+    for (int bi = 0; bi < b; bi++)
+        for (int l = 0; l < c; l++) {
+            float *g = grad_points + ((size_t)bi * c + l) * m;
+            for (int p = 0; p < n; p++) {
+                const int *ix = idx + ((size_t)bi * n + p) * 3;
+                const float *w = weight + ((size_t)bi * n + p) * 3;
+                float go = grad_out[((size_t)bi * c + l) * n + p];
+                g[ix[0]] += go * w[0];
+                g[ix[1]] += go * w[1];
+                g[ix[2]] += go * w[2];
+            }
+        }
+}
+
+/* seg/po/src/grouping/grouping_cuda_kernel.cu:5-14 — output[m,s,c] = input[idx[m,s], c] */
+ORC_API void orc_group_packed_fwd(int m, int nsample, int c, const float *input, const int *idx, float *output)
+{
+#pragma omp parallel for
+    for (long r = 0; r < (long)m * nsample; r++)
+        memcpy(output + r * c, input + (size_t)idx[r] * c, sizeof(float) * c);
+}
+
+/* seg/po/src/grouping/grouping_cuda_kernel.cu:16-25 (R6) */
+ORC_API void orc_group_packed_bwd(int m, int nsample, int c, const float *grad_output, const int *idx,
+                                  float *grad_input)
+{
+    for (long r = 0; r < (long)m * nsample; r++)
+        for (int ch = 0; ch < c; ch++) grad_input[(size_t)idx[r] * c + ch] += grad_output[r * c + ch];
+}
+
+/* seg/po/src/interpolation/interpolation_cuda_kernel.cu:5-18 — output[n,c] += input[idx[n,i],c]*w[n,i]
+ * (output pre-zeroed by the caller; fma(input, w, acc) after contraction) */
+ORC_API void orc_interp_packed_fwd(int n, int c, int k, const float *input, const int *idx, const float *weight,
+                                   float *output)
+{
+#pragma omp parallel for
+    for (long p = 0; p < n; p++)
+        for (int ch = 0; ch < c; ch++) {
+            float acc = output[p * c + ch];
+            for (int i = 0; i < k; i++)
+                acc = fmaf(input[(size_t)idx[p * k + i] * c + ch], weight[p * k + i], acc);
+            output[p * c + ch] = acc;
+        }
+}
+
+/* seg/po/src/interpolation/interpolation_cuda_kernel.cu:20-33 (R6) */
+ORC_API void orc_interp_packed_bwd(int n, int c, int k, const float *grad_output, const int *idx,
+                                   const float *weight, float *grad_input)
+{
+    for (long p = 0; p < n; p++)
+        for (int i = 0; i < k; i++)
+            for (int ch = 0; ch < c; ch++)
+                grad_input[(size_t)idx[p * k + i] * c + ch] += grad_output[p * c + ch] * weight[p * k + i];
+}

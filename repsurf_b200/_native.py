@@ -1,0 +1,97 @@
+"""ctypes binding of librepsurf_b200.so (the C-ABI declared in include/repsurf_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is
+raised.  torch is used for device memory and streams only (data_ptr / current stream handle).
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librepsurf_b200.so")
+_lib = None
+
+_i = ctypes.c_int
+_f = ctypes.c_float
+_p = ctypes.c_void_p
+
+# name -> argtypes (the trailing cudaStream_t is appended automatically)
+_SIGS = {
+    "rsb_furthestsampling_dense": [_i, _i, _i, _p, _p, _p, _p],
+    "rsb_gathering_forward": [_i, _i, _i, _i, _p, _p, _p],
+    "rsb_gathering_backward": [_i, _i, _i, _i, _p, _p, _p],
+    "rsb_ballquery": [_i, _i, _i, _f, _i, _p, _p, _p],
+    "rsb_knnquery_dense": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_knnquery_heap_dense": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_grouping_forward": [_i, _i, _i, _i, _i, _p, _p, _p],
+    "rsb_grouping_backward": [_i, _i, _i, _i, _i, _p, _p, _p],
+    "rsb_grouping_int_forward": [_i, _i, _i, _i, _i, _p, _p, _p],
+    "rsb_nearestneighbor": [_i, _i, _i, _p, _p, _p, _p],
+    "rsb_interpolation_forward": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_interpolation_backward": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_furthestsampling_packed": [_i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],
+    "rsb_grouping_packed_forward": [_i, _i, _i, _p, _p, _p],
+    "rsb_grouping_packed_backward": [_i, _i, _i, _p, _p, _p],
+    "rsb_interpolation_packed_forward": [_i, _i, _i, _p, _p, _p, _p],
+    "rsb_interpolation_packed_backward": [_i, _i, _i, _p, _p, _p, _p],
+}
+EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count"])
+
+
+def build(force=False):
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    env = dict(os.environ)
+    if force:
+        env["FORCE"] = "1"
+    subprocess.check_call(["bash", os.path.join(_HERE, "csrc", "build.sh")], env=env)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(repsurf_b200 has no CPU / PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args + [_p]
+            fn.restype = _i
+        L.rsb_last_error.restype = ctypes.c_char_p
+        L.rsb_launch_count.restype = ctypes.c_ulonglong
+        L.rsb_abi_version.restype = _i
+        _lib = L
+    return _lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("repsurf_b200 kernels take CUDA tensors (no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("repsurf_b200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry on torch's current stream; tensors are passed as device pointers."""
+    L = lib()
+    conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(L, name)(*conv, stream)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (cudaError {rc}): {L.rsb_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib().rsb_launch_count())
+
+
+def reset_launch_count():
+    lib().rsb_reset_launch_count()

@@ -1,0 +1,135 @@
+"""Dense-layout RepSurf-U modules with the reference's constructor / forward signatures and
+state_dict keys (classification/modules/repsurface_utils.py:186-307), running on the sm_100a
+operator layer (`repsurf_b200.cls.pointops`).  CUDA only.
+
+Drop-in: `from repsurf_b200.cls.modules import UmbrellaSurfaceConstructor, SurfaceAbstractionCD`
+replaces `from modules.repsurface_utils import ...` in
+classification/models/repsurf/repsurf_ssg_umb.py:8 (the `cuda=` argument is accepted and ignored:
+there is only the CUDA path).
+
+What differs from the reference implementation (results are the same):
+  * FPS also emits the sampled coordinates (no separate gathering launch), no `.zero_()` pre-fills,
+    no `torch.cuda.empty_cache()` after every op, no permute().contiguous() round trips of the
+    grouped tensor: groups are built channel-first [B,C,m,ns] directly by the grouping kernel.
+  * umbrella geometry is one vectorised routine (repsurf_b200.geometry.umbrella_features).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointops as P
+from ..geometry import umbrella_features, xyz2sphere
+
+
+def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_normal, return_polar):
+    """Sampling + ball-query grouping (reference sample_and_group, repsurface_utils.py:15-59), channel-first.
+    center_cf [B,3,N], normal [B,Cn,N], feature [B,Cf,N]|None ->
+      new_center [B,3,m], new_normal [B,Cn,m], grouped [B, C, m, ns] with C ordered
+      [rel xyz(3), polar(3)?, normal(Cn)?, feature(Cf)?]."""
+    center_cf = center_cf.contiguous()
+    xyz = center_cf.transpose(1, 2).contiguous()                       # [B,N,3] for the query kernels
+    fps_idx, new_xyz = P.furthestsampling_with_xyz(xyz, npoint)         # [B,m], [B,m,3]
+    new_normal = P.gathering(normal.contiguous(), fps_idx)              # [B,Cn,m]
+    idx = P.ballquery(radius, nsample, xyz, new_xyz)                    # [B,m,ns]
+    new_center = new_xyz.transpose(1, 2).contiguous()                   # [B,3,m]
+    rel = P.grouping(center_cf, idx) - new_center.unsqueeze(-1)         # [B,3,m,ns]
+    parts = [rel]
+    if return_polar:
+        parts.append(xyz2sphere(rel.permute(0, 2, 3, 1)).permute(0, 3, 1, 2))
+    if feature is None or return_normal:
+        parts.append(P.grouping(normal.contiguous(), idx))
+    if feature is not None:
+        parts.append(P.grouping(feature.contiguous(), idx))
+    return new_center, new_normal, torch.cat(parts, dim=1)
+
+
+def _all_inputs(center_cf, normal, feature, return_normal, return_polar):
+    """group_all (reference sample_and_group_all, repsurface_utils.py:62-88): one group holding every point,
+    RAW coordinates (not centre-relative), new_center = new_normal = zeros[B,3,1]."""
+    B = center_cf.shape[0]
+    new_center = torch.zeros(B, 3, 1, device=center_cf.device, dtype=center_cf.dtype)
+    parts = [center_cf]
+    if return_polar:
+        parts.append(xyz2sphere(center_cf.transpose(1, 2)).transpose(1, 2))
+    if return_normal:
+        parts.append(normal)
+    parts.append(feature)
+    return new_center, new_center, torch.cat(parts, dim=1).unsqueeze(2)  # [B,C,1,N]
+
+
+class SurfaceAbstractionCD(nn.Module):
+    """ref: classification/modules/repsurface_utils.py:186-249.
+    forward(center [B,3,N], normal [B,Cn,N], feature [B,Cf,N] | None)
+      -> (new_center [B,3,m], new_normal [B,Cn,m], new_feature [B,mlp[-1],m])."""
+
+    def __init__(self, npoint, radius, nsample, feat_channel, pos_channel, mlp, group_all,
+                 return_normal=True, return_polar=False, cuda=True):
+        super().__init__()
+        self.npoint, self.radius, self.nsample = npoint, radius, nsample
+        self.return_normal, self.return_polar = return_normal, return_polar
+        self.pos_channel, self.group_all = pos_channel, group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        self.mlp_l0 = nn.Conv2d(self.pos_channel, mlp[0], 1)
+        self.mlp_f0 = nn.Conv2d(feat_channel, mlp[0], 1)
+        self.bn_l0 = nn.BatchNorm2d(mlp[0])
+        self.bn_f0 = nn.BatchNorm2d(mlp[0])
+        last = mlp[0]
+        for out_channel in mlp[1:]:
+            self.mlp_convs.append(nn.Conv2d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last = out_channel
+
+    def forward(self, center, normal, feature):
+        if self.group_all:
+            new_center, new_normal, x = _all_inputs(center, normal, feature, self.return_normal, self.return_polar)
+        else:
+            new_center, new_normal, x = _grouped_inputs(self.npoint, self.radius, self.nsample, center, normal,
+                                                        feature, self.return_normal, self.return_polar)
+        # channel de-differentiation: position and feature channels get their own first layer (:236-239)
+        x = F.relu(self.bn_l0(self.mlp_l0(x[:, :self.pos_channel])) + self.bn_f0(self.mlp_f0(x[:, self.pos_channel:])))
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            x = F.relu(bn(conv(x)))
+        return new_center, new_normal, torch.max(x, 3)[0]
+
+
+class UmbrellaSurfaceConstructor(nn.Module):
+    """ref: classification/modules/repsurface_utils.py:252-307.
+    forward(center [B,3,N]) -> [B,in_channel,N]."""
+
+    def __init__(self, k, in_channel, aggr_type='sum', return_dist=False, random_inv=True, cuda=True):
+        super().__init__()
+        self.k, self.return_dist, self.random_inv, self.aggr_type = k, return_dist, random_inv, aggr_type
+        self.mlps = nn.Sequential(
+            nn.Conv2d(in_channel, in_channel, 1, bias=False),
+            nn.BatchNorm2d(in_channel),
+            nn.ReLU(True),
+            nn.Conv2d(in_channel, in_channel, 1, bias=True),
+            nn.BatchNorm2d(in_channel),
+            nn.ReLU(True),
+            nn.Conv2d(in_channel, in_channel, 1, bias=True),
+        )
+
+    def forward(self, center):
+        B, _, N = center.shape
+        center_cf = center.contiguous()
+        xyz = center_cf.transpose(1, 2).contiguous()
+        with torch.no_grad():
+            idx = P.knnquery(self.k, xyz, xyz)[:, :, 1:].contiguous()          # drop the query itself (:119)
+            nbr = P.grouping(center_cf, idx)                                    # [B,3,N,G]
+            offsets = (nbr - center_cf.unsqueeze(-1)).permute(0, 2, 3, 1)       # [B,N,G,3]
+            if self.random_inv:
+                # same draw as the reference: CPU generator, one per forward (recons_utils.py:49-51)
+                flip = (torch.randint(0, 2, (B, 1, 1)).float() * 2. - 1.).to(center.device).unsqueeze(-1)
+            else:
+                flip = torch.ones(1, 1, 1, 1, device=center.device)
+            feat = umbrella_features(offsets, flip, rotate_key=False, order="cls")   # [B,N,G,10]
+            if not self.return_dist:
+                feat = feat[..., :9]
+            x = feat.permute(0, 3, 1, 2).contiguous()                           # [B,C,N,G]
+        x = self.mlps(x)
+        if self.aggr_type == 'max':
+            return torch.max(x, 3)[0]
+        if self.aggr_type == 'avg':
+            return torch.mean(x, 3)
+        return torch.sum(x, 3)

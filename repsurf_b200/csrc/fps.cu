@@ -1,0 +1,341 @@
+// fps.cu — farthest point sampling for sm_100a: one thread-block CLUSTER per cloud / segment,
+// the cloud resident in registers for the whole run, one cluster barrier per sample.
+//
+// Replaces (same results, index-exact):
+//   classification/modules/pointops/src/sampling/sampling_cuda_kernel.cu:59-210  (dense  [B,N,3])
+//   segmentation/modules/pointops/src/sampling/sampling_cuda_kernel.cu:15-171    (packed [ΣN,3]+offset)
+//
+// Design (B200-first, not a translation):
+//   * The reference runs ONE block per cloud, re-reads xyz (stride-3 AoS) and read-modify-writes the
+//     running min-distance array in global memory on every one of the m iterations, then does an
+//     11-barrier shared-memory tree.  Here each thread owns PPT points (x,y,z,min-dist) in REGISTERS
+//     for the whole kernel; HBM/L2 is touched once at load time.  A cluster of CS CTAs (up to 16 =
+//     the non-portable maximum) splits one cloud, so a 40 960-point cloud keeps 10 points/thread.
+//   * Per iteration: register scan -> warp arg-max with redux.sync -> every warp leader publishes
+//     (key, x, y, z) of its winner straight into the shared memory of EVERY CTA of the cluster
+//     (st.shared::cluster), ONE barrier.cluster (which also orders the block), then every warp
+//     reduces the CS*warps candidates locally.  No second exchange for the winner's coordinates.
+//   * Exact tie rule R2: the reference's winner among equal maxima is the point
+//     whose (bit-reversed (k mod BS), k) is smallest, BS = its block size.  Points are therefore
+//     loaded in that PRIORITY ORDER (position p <-> original index k), so "smallest position wins"
+//     reproduces the reference bit for bit with a plain (value, ~position) max key.
+//   * Distances use rsb_sqdist (rule R1).
+#include "common.cuh"
+
+namespace {
+
+struct FpsParams {
+    const float *xyz;        // dense: [b, n, 3]; packed: [sum n, 3]
+    const int *offset;       // packed only: cumulative ends [b]
+    const int *new_offset;   // packed only
+    float *temp;             // optional running-min scratch (reference ABI); final values written back
+    int *idx;                // dense: [b, m]; packed: [sum m]
+    float *new_xyz;          // optional fused gather of the sampled coordinates (same layout as idx, x3)
+    int n, m;                // dense sizes (unused when packed)
+    int packed;
+    int bs_ref;              // the REFERENCE's block size (power of two) -> tie rule
+    int log2_bs;
+    const int *n_max_dev;    // optional: device scalar holding the largest segment length; when set the
+                             // reference block size is derived from it in-kernel (no host sync needed)
+    int cs;                  // cluster size
+};
+
+__device__ __forceinline__ int pos2k(uint32_t p, int q_per_thread, int bs_ref, int log2_bs, bool &in_range)
+{
+    // position p = r * Q + q  <->  reference thread t = bitrev(r), q-th point of that thread: k = q*BS + t
+    const uint32_t r = p / (uint32_t)q_per_thread;
+    const uint32_t q = p - r * (uint32_t)q_per_thread;
+    const uint32_t t = log2_bs ? (__brev(r) >> (32 - log2_bs)) : 0u;
+    in_range = r < (uint32_t)bs_ref;
+    return (int)(q * (uint32_t)bs_ref + t);
+}
+
+// PPT > 0: points in registers.  PPT == 0: streaming fallback (min-dist in P.temp, xyz re-read through L2).
+template <int PPT, bool CLUSTER>
+__global__ void __launch_bounds__(PPT == 0 ? 1024 : 512, 1) fps_kernel(FpsParams P)
+{
+    extern __shared__ __align__(16) unsigned char fps_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const uint32_t cs = CLUSTER ? (uint32_t)P.cs : 1u;
+    const uint32_t rank = CLUSTER ? rsb_cluster_ctarank() : 0u;
+    const int seg = CLUSTER ? (int)rsb_cluster_id_x() : (int)blockIdx.x;
+    const int E = (int)cs * nwarps;  // candidates per iteration
+    if (P.n_max_dev) {  // floor(log2(n_max)) capped at 10 == the reference's libm expression (checked for n < 5000)
+        const int nm = max(__ldg(P.n_max_dev), 1);
+        P.log2_bs = min(31 - __clz(nm), 10);
+        P.bs_ref = 1 << P.log2_bs;
+    }
+    uint2 *keys = reinterpret_cast<uint2 *>(fps_smem);                       // [2][E]
+    float4 *crd = reinterpret_cast<float4 *>(fps_smem + sizeof(uint2) * 2 * E);  // [2][E]
+
+    // ---- segment descriptor ------------------------------------------------------------------
+    int start_n, n_seg, start_m, m_seg, index_base;
+    if (P.packed) {
+        start_n = seg ? P.offset[seg - 1] : 0;
+        n_seg = P.offset[seg] - start_n;
+        start_m = seg ? P.new_offset[seg - 1] : 0;
+        m_seg = P.new_offset[seg] - start_m;
+        index_base = start_n;
+    } else {
+        start_n = seg * P.n;
+        n_seg = P.n;
+        start_m = seg * P.m;
+        m_seg = P.m;
+        index_base = 0;
+    }
+    const float *xyz = P.xyz + (size_t)start_n * 3;
+    int *out = P.idx + start_m;
+    float *out_xyz = P.new_xyz ? P.new_xyz + (size_t)start_m * 3 : nullptr;
+    float *temp = P.temp ? P.temp + start_n : nullptr;
+    if (n_seg <= 0 || m_seg <= 0) return;  // whole cluster takes this branch together
+
+    const uint32_t T = cs * blockDim.x;
+    const uint32_t g = rank * blockDim.x + tid;
+    const int Q = (n_seg + P.bs_ref - 1) / P.bs_ref;
+    const uint32_t npos = (uint32_t)Q * (uint32_t)P.bs_ref;
+
+    // ---- load (priority order) -----------------------------------------------------------------
+    constexpr int R = PPT > 0 ? PPT : 1;
+    float px[R], py[R], pz[R], md[R];
+    if (PPT > 0) {
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const uint32_t p = g + (uint32_t)j * T;
+            bool in_range;
+            const int k = pos2k(p, Q, P.bs_ref, P.log2_bs, in_range);
+            const bool valid = in_range && k < n_seg;
+            px[j] = valid ? __ldg(xyz + (size_t)k * 3 + 0) : 0.f;
+            py[j] = valid ? __ldg(xyz + (size_t)k * 3 + 1) : 0.f;
+            pz[j] = valid ? __ldg(xyz + (size_t)k * 3 + 2) : 0.f;
+            md[j] = valid ? 1e10f : -1.f;  // fminf(d, -1) stays -1: never beats a real point
+        }
+    } else {
+        for (uint32_t p = g; p < npos; p += T) {
+            bool in_range;
+            const int k = pos2k(p, Q, P.bs_ref, P.log2_bs, in_range);
+            if (in_range && k < n_seg) temp[k] = 1e10f;
+        }
+        if (CLUSTER) { rsb_cluster_arrive_release(); rsb_cluster_wait_acquire(); } else __syncthreads();
+    }
+
+    float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // first sample: row 0 (k = 0)
+    if (g == 0) {
+        out[0] = index_base;
+        if (out_xyz) { out_xyz[0] = cx; out_xyz[1] = cy; out_xyz[2] = cz; }
+    }
+
+    for (int it = 1; it < m_seg; it++) {
+        // ---- thread-local scan: first strict maximum in position order ---------------------------
+        float best = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+        uint32_t bp = g;
+        if (PPT > 0) {
+            int bj = 0;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const float d = rsb_sqdist(px[j], py[j], pz[j], cx, cy, cz);
+                const float d2 = fminf(d, md[j]);
+                md[j] = d2;
+                const bool gt = d2 > best;
+                best = gt ? d2 : best;
+                bj = gt ? j : bj;
+                bx = gt ? px[j] : bx;
+                by = gt ? py[j] : by;
+                bz = gt ? pz[j] : bz;
+            }
+            bp = g + (uint32_t)bj * T;
+        } else {
+            for (uint32_t p = g; p < npos; p += T) {
+                bool in_range;
+                const int k = pos2k(p, Q, P.bs_ref, P.log2_bs, in_range);
+                if (!(in_range && k < n_seg)) continue;
+                const float x = xyz[(size_t)k * 3], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
+                const float d2 = fminf(rsb_sqdist(x, y, z, cx, cy, cz), temp[k]);
+                temp[k] = d2;
+                if (d2 > best) { best = d2; bp = p; bx = x; by = y; bz = z; }
+            }
+        }
+        // key: value bits (+1 so that "no point" = 0 sorts below d2 = +0), then ~position (smaller wins)
+        const uint32_t hi = best >= 0.f ? __float_as_uint(best) + 1u : 0u;
+        const uint32_t lo = ~bp;
+        // ---- warp arg-max ------------------------------------------------------------------------
+        const uint32_t whi = __reduce_max_sync(0xffffffffu, hi);
+        const uint32_t wlo = __reduce_max_sync(0xffffffffu, hi == whi ? lo : 0u);
+        const int src = __ffs(__ballot_sync(0xffffffffu, hi == whi && lo == wlo)) - 1;
+        const float wx = __shfl_sync(0xffffffffu, bx, src);
+        const float wy = __shfl_sync(0xffffffffu, by, src);
+        const float wz = __shfl_sync(0xffffffffu, bz, src);
+        // ---- publish to every CTA of the cluster, one barrier --------------------------------------
+        const int par = it & 1;
+        const int slot = par * E + (int)rank * nwarps + warp;
+        if (CLUSTER) {
+            if ((uint32_t)lane < cs) {
+                rsb_st_cluster_v2(rsb_mapa(rsb_smem_addr(&keys[slot]), lane), whi, wlo);
+                rsb_st_cluster_v4(rsb_mapa(rsb_smem_addr(&crd[slot]), lane), __float_as_uint(wx),
+                                  __float_as_uint(wy), __float_as_uint(wz), 0u);
+            }
+            rsb_cluster_arrive_release();
+            rsb_cluster_wait_acquire();
+        } else {
+            if (lane == 0) {
+                keys[slot] = make_uint2(whi, wlo);
+                crd[slot] = make_float4(wx, wy, wz, 0.f);
+            }
+            __syncthreads();
+        }
+        // ---- every warp reduces the E candidates ---------------------------------------------------
+        uint32_t khi = 0, klo = 0;
+        int ke = 0;
+        for (int e = lane; e < E; e += 32) {
+            const uint2 k = keys[par * E + e];
+            const bool gt = k.x > khi || (k.x == khi && k.y > klo);
+            khi = gt ? k.x : khi;
+            klo = gt ? k.y : klo;
+            ke = gt ? e : ke;
+        }
+        const uint32_t fhi = __reduce_max_sync(0xffffffffu, khi);
+        const uint32_t flo = __reduce_max_sync(0xffffffffu, khi == fhi ? klo : 0u);
+        const int wsrc = __ffs(__ballot_sync(0xffffffffu, khi == fhi && klo == flo)) - 1;
+        const int we = __shfl_sync(0xffffffffu, ke, wsrc);
+        const float4 c = crd[par * E + we];
+        cx = c.x; cy = c.y; cz = c.z;
+        if (g == 0) {
+            bool in_range;
+            const int k = pos2k(~flo, Q, P.bs_ref, P.log2_bs, in_range);
+            out[it] = index_base + k;
+            if (out_xyz) { out_xyz[it * 3] = cx; out_xyz[it * 3 + 1] = cy; out_xyz[it * 3 + 2] = cz; }
+        }
+    }
+
+    // reference ABI: `temp` holds the final running minima (callers discard it)
+    if (PPT > 0 && temp) {
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const uint32_t p = g + (uint32_t)j * T;
+            bool in_range;
+            const int k = pos2k(p, Q, P.bs_ref, P.log2_bs, in_range);
+            if (in_range && k < n_seg) temp[k] = md[j];
+        }
+    }
+}
+
+struct FpsPlan {
+    int cs, nt, ppt;
+};
+
+// Choose (cluster size, threads, points/thread) for the largest segment.
+FpsPlan fps_plan(int n_max)
+{
+    FpsPlan pl;
+    if (n_max <= 256) { pl.cs = 1; pl.nt = 64; }
+    else if (n_max <= 1024) { pl.cs = 1; pl.nt = 128; }
+    else if (n_max <= 4096) { pl.cs = 1; pl.nt = 256; }
+    else if (n_max <= 8192) { pl.cs = 2; pl.nt = 512; }
+    else if (n_max <= 16384) { pl.cs = 4; pl.nt = 512; }
+    else if (n_max <= 65536) { pl.cs = 8; pl.nt = 512; }
+    else { pl.cs = 16; pl.nt = 512; }
+    const long cap = (long)pl.cs * pl.nt;
+    pl.ppt = (int)((n_max + cap - 1) / cap);
+    if (pl.ppt > 16) { pl.cs = 16; pl.nt = 1024; pl.ppt = 0; }  // streaming fallback
+    return pl;
+}
+
+template <int PPT>
+int fps_launch_ppt(const FpsParams &P, int nseg, const FpsPlan &pl, cudaStream_t stream)
+{
+    const size_t smem = (size_t)(sizeof(uint2) + sizeof(float4)) * 2 * pl.cs * (pl.nt / 32);
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(pl.nt);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (pl.cs > 1) {
+        auto kern = fps_kernel<PPT, true>;
+        if (pl.cs > 8) RSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cfg.gridDim = dim3(nseg * pl.cs);
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pl.cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        RSB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    } else {
+        cfg.gridDim = dim3(nseg);
+        cfg.attrs = nullptr;
+        cfg.numAttrs = 0;
+        RSB_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<PPT, false>, P));
+    }
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+int fps_launch(FpsParams P, int nseg, int n_max, cudaStream_t stream)
+{
+    FpsPlan pl = fps_plan(n_max);
+    if (const char *e = getenv("RSB_FPS_PLAN")) {  // tuning hook: "cs,nt"
+        int cs = 0, nt = 0;
+        if (sscanf(e, "%d,%d", &cs, &nt) == 2 && cs >= 1 && cs <= 16 && nt >= 32 && nt <= 512 && nt % 32 == 0) {
+            long cap = (long)cs * nt;
+            int ppt = (int)((n_max + cap - 1) / cap);
+            if (ppt <= 16) { pl.cs = cs; pl.nt = nt; pl.ppt = ppt; }
+        }
+    }
+    P.cs = pl.cs;
+    if (pl.ppt == 0) RSB_REQUIRE(P.temp != nullptr, "segments beyond the register-resident capacity need the temp scratch buffer");
+    switch (pl.ppt) {
+#define RSB_CASE(N) case N: return fps_launch_ppt<N>(P, nseg, pl, stream);
+        RSB_CASE(0) RSB_CASE(1) RSB_CASE(2) RSB_CASE(3) RSB_CASE(4) RSB_CASE(5) RSB_CASE(6) RSB_CASE(7) RSB_CASE(8)
+        RSB_CASE(9) RSB_CASE(10) RSB_CASE(11) RSB_CASE(12) RSB_CASE(13) RSB_CASE(14) RSB_CASE(15) RSB_CASE(16)
+#undef RSB_CASE
+    }
+    rsb_set_error("fps: no plan for n_max=%d", n_max);
+    return (int)cudaErrorInvalidValue;
+}
+
+// classification/modules/pointops/src/cuda_utils.h:15-18 (same libm expression => same block size)
+int ref_opt_n_threads(int work_size)
+{
+    const int pow_2 = (int)(std::log(static_cast<double>(work_size)) / std::log(2.0));
+    int v = 1 << pow_2;
+    if (v > 1024) v = 1024;
+    if (v < 1) v = 1;
+    return v;
+}
+
+int ilog2(int v)
+{
+    int l = 0;
+    while ((1 << (l + 1)) <= v) l++;
+    return l;
+}
+
+}  // namespace
+
+RSB_EXPORT int rsb_furthestsampling_dense(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                          float *new_xyz, cudaStream_t stream)
+{
+    RSB_REQUIRE(b >= 0 && n >= 1 && m >= 0, "bad sizes");
+    if (b == 0 || m == 0) return 0;
+    FpsParams P = {};
+    P.xyz = xyz; P.temp = temp; P.idx = idx; P.new_xyz = new_xyz;
+    P.n = n; P.m = m; P.packed = 0;
+    P.bs_ref = ref_opt_n_threads(n);
+    P.log2_bs = ilog2(P.bs_ref);
+    return fps_launch(P, b, n, stream);
+}
+
+RSB_EXPORT int rsb_furthestsampling_packed(int b, int n_max, const int *n_max_dev, const float *xyz,
+                                           const int *offset, const int *new_offset, float *tmp, int *idx,
+                                           float *new_xyz, cudaStream_t stream)
+{
+    RSB_REQUIRE(b >= 0 && n_max >= 1, "bad sizes");
+    if (b == 0) return 0;
+    FpsParams P = {};
+    P.xyz = xyz; P.offset = offset; P.new_offset = new_offset; P.temp = tmp; P.idx = idx; P.new_xyz = new_xyz;
+    P.packed = 1;
+    P.n_max_dev = n_max_dev;
+    P.bs_ref = ref_opt_n_threads(n_max);
+    P.log2_bs = ilog2(P.bs_ref);
+    return fps_launch(P, b, n_max, stream);
+}

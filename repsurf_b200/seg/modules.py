@@ -1,0 +1,162 @@
+"""Packed-layout RepSurf-U modules with the reference's constructor / forward signatures and
+state_dict keys (segmentation/modules/repsurface_utils.py:176-329), running on the sm_100a operator
+layer (`repsurf_b200.seg.pointops`).  CUDA only.
+
+Drop-in: `from repsurf_b200.seg.modules import UmbrellaSurfaceConstructor, SurfaceAbstractionCD,
+SurfaceFeaturePropagationCD` replaces `from modules.repsurface_utils import ...` in
+segmentation/models/repsurf/repsurf_umb_ssg.py:8.
+
+Differences from the reference implementation (same results):
+  * no per-cloud `.item()` round trips: offsets keep a host mirror (pointops.host_offsets),
+    strided offsets are computed on the host once and uploaded asynchronously;
+  * sectorized FPS runs fully on the device (pointops.sectorized_fps);
+  * FPS emits the sampled coordinates; kNN emits sqrt distances; gathers use the grouping kernel.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointops as P
+from ..geometry import umbrella_features, xyz2sphere
+
+
+def strided_offsets(offset, stride):
+    """new_n_i = n_i // stride, cumulative (segmentation/modules/repsurface_utils.py:17-22), host arithmetic."""
+    off = P.host_offsets(offset)
+    acc, out, prev = 0, [], 0
+    for o in off:
+        acc += (o - prev) // stride
+        out.append(acc)
+        prev = o
+    return P.make_offsets(out, offset.device)
+
+
+def _sample_and_group(stride, nsample, center, normal, feature, offset, return_polar, num_sector, training):
+    """ref: segmentation/modules/repsurface_utils.py:15-51.
+    -> new_center [M,3], new_normal [M,Cn], grouped [M,ns,C] (C = [rel xyz, polar?, normal, feature?]), new_offset."""
+    if stride > 1:
+        new_offset = strided_offsets(offset, stride)
+        if num_sector > 1 and training:
+            fps_idx = P.sectorized_fps(center, offset, new_offset, num_sector)
+        else:
+            fps_idx = P.furthestsampling(center, offset, new_offset)
+        fps_idx = fps_idx.long()
+        new_center = center[fps_idx, :]
+        new_normal = normal[fps_idx, :]
+    else:
+        new_center, new_normal, new_offset = center, normal, offset
+    group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
+    rel = P.grouping(center, group_idx) - new_center.unsqueeze(1)
+    parts = [rel]
+    if return_polar:
+        parts.append(xyz2sphere(rel))
+    parts.append(P.grouping(normal.contiguous(), group_idx))
+    if feature is not None:
+        parts.append(P.grouping(feature.contiguous(), group_idx))
+    return new_center, new_normal, torch.cat(parts, dim=-1), new_offset
+
+
+class SurfaceAbstractionCD(nn.Module):
+    """ref: segmentation/modules/repsurface_utils.py:176-230.
+    forward([center [N,3], normal [N,Cn], feature [N,C], offset [B]])
+      -> [new_center [M,3], new_normal [M,Cn], new_feature [M,mlp[-1]], new_offset [B]]."""
+
+    def __init__(self, stride, nsample, feat_channel, pos_channel, mlp, return_normal=True, return_polar=False,
+                 num_sector=1):
+        super().__init__()
+        self.stride, self.nsample = stride, nsample
+        self.return_normal, self.return_polar, self.num_sector = return_normal, return_polar, num_sector
+        self.pos_channel = pos_channel
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        self.mlp_l0 = nn.Conv1d(self.pos_channel, mlp[0], 1)
+        self.mlp_f0 = nn.Conv1d(feat_channel, mlp[0], 1)
+        self.bn_l0 = nn.BatchNorm1d(mlp[0])
+        self.bn_f0 = nn.BatchNorm1d(mlp[0])
+        last = mlp[0]
+        for out_channel in mlp[1:]:
+            self.mlp_convs.append(nn.Conv1d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last = out_channel
+
+    def forward(self, pos_nor_feat_off):
+        center, normal, feature, offset = pos_nor_feat_off
+        new_center, new_normal, x, new_offset = _sample_and_group(
+            self.stride, self.nsample, center, normal, feature, offset, self.return_polar, self.num_sector,
+            self.training)
+        x = x.transpose(1, 2).contiguous()                                  # [M,C,ns]
+        x = F.relu(self.bn_l0(self.mlp_l0(x[:, :self.pos_channel])) + self.bn_f0(self.mlp_f0(x[:, self.pos_channel:])))
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            x = F.relu(bn(conv(x)))
+        return [new_center, new_normal, torch.max(x, 2)[0], new_offset]
+
+
+class SurfaceFeaturePropagationCD(nn.Module):
+    """ref: segmentation/modules/repsurface_utils.py:233-284.
+    forward([xyz1 [N,3], points1 [N,C1]|None, offset1], [xyz2 [M,3], points2 [M,C2], offset2]) -> [N, mlp[-1]]."""
+
+    def __init__(self, prev_channel, skip_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        self.skip = skip_channel is not None
+        self.mlp_f0 = nn.Linear(prev_channel, mlp[0])
+        self.norm_f0 = nn.BatchNorm1d(mlp[0])
+        if skip_channel is not None:
+            self.mlp_s0 = nn.Linear(skip_channel, mlp[0])
+            self.norm_s0 = nn.BatchNorm1d(mlp[0])
+        last = mlp[0]
+        for out_channel in mlp[1:]:
+            self.mlp_convs.append(nn.Linear(last, out_channel))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last = out_channel
+
+    def forward(self, pos_feat_off1, pos_feat_off2):
+        xyz1, points1, offset1 = pos_feat_off1
+        xyz2, points2, offset2 = pos_feat_off2
+        idx, dist = P.knnquery(3, xyz2, xyz1, offset2, offset1)             # coarse neighbours of every fine point
+        weight = P._idw(dist).contiguous()
+        coarse = self.norm_f0(self.mlp_f0(points2))                         # projected BEFORE interpolation (:267)
+        x = P._InterpApply.apply(coarse, idx, weight)
+        if self.skip:
+            x = x + self.norm_s0(self.mlp_s0(points1))
+        x = F.relu(x)
+        for lin, bn in zip(self.mlp_convs, self.mlp_bns):
+            x = F.relu(bn(lin(x)))
+        return x
+
+
+class UmbrellaSurfaceConstructor(nn.Module):
+    """ref: segmentation/modules/repsurface_utils.py:287-329.
+    forward(center [N,3], offset [B]) -> [N,out_channel]."""
+
+    def __init__(self, k, in_channel, out_channel, random_inv=True, sort='fix'):
+        super().__init__()
+        if sort not in (None, 'fix'):
+            raise Exception('No such sorting method')
+        self.k, self.random_inv, self.sort = k, random_inv, sort
+        self.mlps = nn.Sequential(
+            nn.Conv1d(in_channel, out_channel, 1, bias=True),
+            nn.BatchNorm1d(out_channel),
+            nn.ReLU(True),
+            nn.Conv1d(out_channel, out_channel, 1, bias=True),
+        )
+
+    def forward(self, center, offset):
+        with torch.no_grad():
+            # all k neighbours are kept, the query itself included (the reference takes no [:, 1:] slice)
+            idx, _ = P.knnquery(self.k, center, center, offset, offset)
+            offsets = P.grouping(center, idx) - center.unsqueeze(1)         # [N,k,3]
+            if self.random_inv:
+                # same draw as the reference: numpy global RNG, one value per cloud (recons_utils.py:28-37)
+                keep = np.random.rand(offset.shape[0]) < 0.5
+                sizes = P._sizes(P.host_offsets(offset))
+                sign = torch.from_numpy(np.where(keep, 1.0, -1.0).astype(np.float32)).to(center.device, non_blocking=True)
+                flip = torch.repeat_interleave(sign, torch.tensor(sizes, device=center.device),
+                                               output_size=center.shape[0]).view(-1, 1, 1)
+            else:
+                flip = torch.ones(1, 1, 1, device=center.device)
+            feat = umbrella_features(offsets, flip, rotate_key=(self.sort == 'fix'), order="seg")  # [N,k,10]
+            x = feat.transpose(1, 2).contiguous()                            # [N,10,k]
+        return torch.sum(self.mlps(x), 2)

@@ -1,0 +1,235 @@
+"""Packed-layout operator API — same names and argument meaning as the reference's
+segmentation/modules/pointops/functions/pointops.py (cited per op), backed by librepsurf_b200.so.
+
+Packed layout: coord [N,3], feat [N,C], offset [B] int32 cumulative ends (device tensor).
+
+Host synchronisation.  The reference reads `offset` element by element on the host
+(`offset[i].item()`, tensor `max()` in Python loops: pointops.py:39-42, 61-93).  Here the host
+copy of an offset tensor is taken ONCE (`host_offsets`) and remembered for tensors created by
+this package (`register_offsets`), so a forward pass performs no device->host round trips after
+the first look at the input offsets.
+"""
+import weakref
+
+import torch
+from torch.autograd import Function
+
+from .. import _native as N
+
+# ---------------------------------------------------------------------------------------------
+# host copies of offset tensors
+# ---------------------------------------------------------------------------------------------
+_HOST = {}
+
+
+def register_offsets(t, values):
+    """Remember the host values of an offset tensor created by this package (treated as immutable)."""
+    key = id(t)
+    _HOST[key] = (weakref.ref(t, lambda _r, k=key: _HOST.pop(k, None)), tuple(int(v) for v in values))
+    return t
+
+
+def host_offsets(t):
+    ent = _HOST.get(id(t))
+    if ent is not None and ent[0]() is t:
+        return ent[1]
+    vals = tuple(t.tolist())  # one D2H sync, only for offsets that came from outside
+    register_offsets(t, vals)
+    return vals
+
+
+def make_offsets(values, device):
+    t = torch.tensor(list(values), dtype=torch.int32, device=device)
+    return register_offsets(t, values)
+
+
+def _sizes(off):
+    return [b - a for a, b in zip((0,) + tuple(off[:-1]), off)]
+
+
+# ---------------------------------------------------------------------------------------------
+class FurthestSampling(Function):
+    """ref: pointops.py:31-49.  xyz (n,3), offset (b), new_offset (b) -> idx (m) int32, GLOBAL row ids."""
+
+    @staticmethod
+    def forward(ctx, xyz, offset, new_offset):
+        assert xyz.is_contiguous()
+        off, noff = host_offsets(offset), host_offsets(new_offset)
+        b = len(off)
+        idx = torch.empty(noff[-1], dtype=torch.int32, device=xyz.device)
+        N.call("rsb_furthestsampling_packed", b, max(_sizes(off)), None, xyz, offset, new_offset, None, idx, None)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None
+
+
+furthestsampling = FurthestSampling.apply
+
+
+def _linspace_f32(start, end, steps):
+    """torch.linspace(start, end, steps) in fp32, element by element as ATen's CPU kernel computes it
+    (aten/src/ATen/native/RangeFactories.cpp: step=(end-start)/(steps-1); i < steps/2 ? start+step*i :
+    end-step*(steps-1-i)), vectorised over clouds: start/end are [B] tensors -> [B, steps]."""
+    step = (end - start) / float(steps - 1)
+    i = torch.arange(steps, device=start.device, dtype=torch.float32)
+    lo = start[:, None] + step[:, None] * i[None, :]
+    hi = end[:, None] - step[:, None] * (float(steps - 1) - i)[None, :]
+    return torch.where((i < steps // 2)[None, :], lo, hi)
+
+
+class SectorizedFurthestSampling(Function):
+    """ref: pointops.py:52-111.  Azimuth-sectorized FPS; returns int64 global row ids, sector-major per cloud.
+
+    The reference does the sector split in host Python (per cloud and per sector `torch.where`,
+    `.item()`); here it is a handful of device ops (segment min/max, bucket, stable sort) followed by
+    ONE packed FPS launch over all (cloud, sector) segments, with no host synchronisation: the sector
+    sizes stay on the device and the kernel derives the reference's tie rule from the device-side
+    maximum (rsb_furthestsampling_packed n_max_dev)."""
+
+    @staticmethod
+    def forward(ctx, xyz, offset, new_offset, num_sectors, min_points=10000):
+        assert xyz.is_contiguous()
+        dev = xyz.device
+        off, noff = host_offsets(offset), host_offsets(new_offset)
+        sizes, new_sizes = _sizes(off), _sizes(noff)
+        b = len(off)
+        n = xyz.shape[0]
+        nsec = [1 if s < min_points else num_sectors for s in sizes]          # host, from host offsets
+        quotas, seg_first = [], []
+        for i in range(b):
+            q = [new_sizes[i] // nsec[i]] * nsec[i]
+            q[-1] += new_sizes[i] % nsec[i]
+            seg_first.append(len(quotas))
+            quotas += q
+        nseg = len(quotas)
+        new_sector_offset = torch.tensor(quotas, dtype=torch.int64).cumsum(0).to(torch.int32).to(dev, non_blocking=True)
+
+        cloud = torch.repeat_interleave(torch.arange(b, device=dev), torch.tensor(sizes, device=dev), output_size=n)
+        angle = torch.atan2(xyz[:, 0], xyz[:, 1])
+        amin = torch.full((b,), float("inf"), device=dev).scatter_reduce_(0, cloud, angle, "amin")
+        amax = torch.full((b,), float("-inf"), device=dev).scatter_reduce_(0, cloud, angle, "amax")
+        edges = _linspace_f32(amin, amax + 1e-4, num_sectors + 1)              # [b, S+1]
+        # sector s  <=>  edges[s] <= angle < edges[s+1]   (count of inner edges <= angle)
+        sec = (angle[:, None] >= edges[cloud][:, 1:num_sectors]).sum(1)
+        nsec_t = torch.tensor(nsec, device=dev)
+        sec = torch.where(nsec_t[cloud] > 1, sec, torch.zeros_like(sec))
+        seg_id = torch.tensor(seg_first, device=dev)[cloud] + sec
+        order = torch.sort(seg_id, stable=True)[1]                             # sector-major, ascending index inside
+        counts = torch.bincount(seg_id, minlength=nseg)
+        sector_offset = counts.cumsum(0).to(torch.int32)
+        n_max_dev = counts.max().to(torch.int32).reshape(1)
+        sector_xyz = xyz[order].contiguous()
+        idx = torch.empty(noff[-1], dtype=torch.int32, device=dev)
+        N.call("rsb_furthestsampling_packed", nseg, max(sizes), n_max_dev, sector_xyz, sector_offset,
+               new_sector_offset, None, idx, None)
+        out = order[idx.long()]
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None, None
+
+
+sectorized_fps = SectorizedFurthestSampling.apply
+
+
+class KNNQuery(Function):
+    """ref: pointops.py:114-130.  -> (idx (m,nsample) int32 global ids, sqrt(dist2) (m,nsample))."""
+
+    @staticmethod
+    def forward(ctx, nsample, xyz, new_xyz, offset, new_offset):
+        if new_xyz is None:
+            new_xyz = xyz
+        assert xyz.is_contiguous() and new_xyz.is_contiguous()
+        m = new_xyz.shape[0]
+        idx = torch.empty(m, nsample, dtype=torch.int32, device=xyz.device)
+        dist = torch.empty(m, nsample, dtype=torch.float32, device=xyz.device)
+        N.call("rsb_knnquery_packed", offset.shape[0], m, int(nsample), xyz, new_xyz, offset, new_offset, idx, dist, 1)
+        ctx.mark_non_differentiable(idx, dist)
+        return idx, dist
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None, None, None, None
+
+
+knnquery = KNNQuery.apply
+
+
+class Grouping(Function):
+    """ref: pointops.py:133-162.  input (n,c), idx (m,nsample) -> (m,nsample,c)."""
+
+    @staticmethod
+    def forward(ctx, input, idx):
+        assert input.is_contiguous() and idx.is_contiguous()
+        m, nsample, n, c = idx.shape[0], idx.shape[1], input.shape[0], input.shape[1]
+        out = torch.empty(m, nsample, c, dtype=torch.float32, device=input.device)
+        N.call("rsb_grouping_packed_forward", m, nsample, c, input, idx, out)
+        ctx.n = n
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        idx, = ctx.saved_tensors
+        m, nsample, c = grad_output.shape
+        grad = torch.zeros(ctx.n, c, dtype=torch.float32, device=grad_output.device)
+        N.call("rsb_grouping_packed_backward", m, nsample, c, grad_output.contiguous(), idx, grad)
+        return grad, None
+
+
+grouping = Grouping.apply
+
+
+def queryandgroup(nsample, xyz, new_xyz, feat, idx, offset, new_offset, use_xyz=True):
+    """ref: pointops.py:165-186.  -> (m, nsample, 3+c) (or (m,nsample,c))."""
+    assert xyz.is_contiguous() and feat.is_contiguous()
+    if new_xyz is None:
+        new_xyz = xyz
+    if idx is None:
+        idx, _ = knnquery(nsample, xyz, new_xyz, offset, new_offset)
+    grouped_xyz = grouping(xyz, idx) - new_xyz.unsqueeze(1)
+    grouped_feat = grouping(feat, idx)
+    return torch.cat((grouped_xyz, grouped_feat), -1) if use_xyz else grouped_feat
+
+
+def _idw(dist):
+    """inverse-distance weights of pointops.py:262-265 / 283-285 (un-squared distance, eps 1e-8)."""
+    r = 1.0 / (dist + 1e-8)
+    return r / torch.sum(r, dim=1, keepdim=True)
+
+
+class _InterpApply(Function):
+    @staticmethod
+    def forward(ctx, input, idx, weight):
+        n, k = idx.shape
+        m, c = input.shape
+        out = torch.zeros(n, c, dtype=torch.float32, device=input.device)
+        N.call("rsb_interpolation_packed_forward", n, c, k, input.contiguous(), idx, weight, out)
+        ctx.m = m
+        ctx.save_for_backward(idx, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        idx, weight = ctx.saved_tensors
+        n, c = grad_output.shape
+        grad = torch.zeros(ctx.m, c, dtype=torch.float32, device=grad_output.device)
+        N.call("rsb_interpolation_packed_backward", n, c, idx.shape[1], grad_output.contiguous(), idx, weight, grad)
+        return grad, None, None
+
+
+def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
+    """ref: pointops.py:256-270.  xyz (m,3), new_xyz (n,3), feat (m,c) -> (n,c)."""
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and feat.is_contiguous()
+    idx, dist = knnquery(k, xyz, new_xyz, offset, new_offset)
+    return _InterpApply.apply(feat, idx, _idw(dist).contiguous())
+
+
+def interpolation2(xyz, new_xyz, input, offset, new_offset, k=3):
+    """ref: pointops.py:273-307 (the autograd.Function variant; same result as `interpolation`)."""
+    return interpolation(xyz, new_xyz, input, offset, new_offset, k)
