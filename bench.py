@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — RepSurf-U fwd+bwd(+SGD step) throughput on synthetic clouds, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload seg|cls] [--impl reference]
+
+Prints ONE JSON line (rank 0).  Contract: see the task statement / DESIGN.md "Measurement".
+  value         clouds/sec, whole job, inputs already resident in HBM
+  e2e           same metric through the public module API with HOST (pinned) inputs: H2D of the step's
+                inputs and D2H of the loss inside the timed region
+  roofline      the dominant repsurf_b200 kernel, timed with CUDA events inside the timed region
+  cpu_baseline  the oracle port (oracle/model_ref.py + oracle C) on the host cores, bounded sample
+  --impl reference   times that CPU port alone (the reference has no CPU path for segmentation and
+                     /root/reference does not exist on the GPU box)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+# -------------------------------------------------------------------------------------------- workloads
+WORKLOADS = {
+    # BASELINE.json configs[2]/[3]: RepSurf-U S3DIS seg, B=8 clouds x N=40960 per GPU, training mode
+    "seg": dict(name="RepSurf-U S3DIS seg (repsurf_umb_ssg), B=8 x N=40960 per GPU, fwd+bwd+SGD", clouds=8, n=40960),
+    # BASELINE.json configs[1]: RepSurf-U ScanObjectNN cls, B=32, N=1024
+    "cls": dict(name="RepSurf-U ScanObjectNN cls (repsurf_ssg_umb), B=32 x N=1024 per GPU, fwd+bwd+SGD", clouds=32, n=1024),
+}
+
+
+def make_inputs(workload, clouds, n, seed, pin):
+    """Synthetic data of SURVEY.md §8(d): seg coord=rand*[8,8,3] mean-centred per cloud, feat=randn, 13 classes;
+    cls points=rand*2-1, 15 classes.  Host tensors (pinned when asked)."""
+    g = torch.Generator().manual_seed(seed)
+    if workload == "seg":
+        coord = torch.rand(clouds * n, 3, generator=g) * torch.tensor([8.0, 8.0, 3.0])
+        coord = (coord.view(clouds, n, 3) - coord.view(clouds, n, 3).mean(1, keepdim=True)).reshape(-1, 3).contiguous()
+        feat = torch.randn(clouds * n, 3, generator=g)
+        target = torch.randint(0, 13, (clouds * n,), generator=g)
+        offset = (torch.arange(1, clouds + 1) * n).int()
+        ts = [coord, feat, offset, target]
+    else:
+        pts = torch.rand(clouds, 3, n, generator=g) * 2 - 1
+        target = torch.randint(0, 15, (clouds,), generator=g)
+        ts = [pts, target]
+    if pin:
+        ts = [t.pin_memory() for t in ts]
+    return ts
+
+
+# -------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------- per-entry timing
+class EntryTimer:
+    """CUDA-event timing of every C-ABI call made through repsurf_b200._native.call (torch's current stream)."""
+
+    def __init__(self, native):
+        self.native, self.orig, self.ev = native, native.call, []
+
+    def __enter__(self):
+        def timed(name, *args):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            self.orig(name, *args)
+            b.record()
+            self.ev.append((name, args[:5], a, b))
+        self.native.call = timed
+        return self
+
+    def __exit__(self, *exc):
+        self.native.call = self.orig
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, args, a, b in self.ev:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "each": []})
+            t = a.elapsed_time(b)
+            d["ms"] += t
+            d["calls"] += 1
+            d["each"].append((args, t))
+        return out
+
+
+# -------------------------------------------------------------------------------------------- algorithmic work
+def fps_algorithmic_bytes(n, m):
+    """SURVEY.md §8(d) streaming model: (m-1) * n * 20 B (12 B xyz + 4 B read + 4 B write of the running
+    minimum) + 4 m B of indices, per segment."""
+    return (m - 1) * n * 20 + 4 * m
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# -------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_run(workload, steps, warmup, sample_clouds, sample_n):
+    """fwd+bwd of the oracle port on the host cores over a bounded sample; returns (clouds/s, seconds/step, cores)."""
+    from oracle import model_ref as MR
+    from oracle import oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cores = max(torch.get_num_threads(), O.num_threads())
+    torch.manual_seed(0)
+    np.random.seed(0)
+    if workload == "seg":
+        model = MR.SegNet().train()
+        coord, feat, offset, target = make_inputs("seg", sample_clouds, sample_n, 0, False)
+        crit = nn.CrossEntropyLoss()
+        def step():
+            model.zero_grad(set_to_none=True)
+            crit(model([coord, feat, offset]), target).backward()
+    else:
+        from repsurf_b200.models import SmoothClsLoss
+        model = MR.ClsNet().train()
+        pts, target = make_inputs("cls", sample_clouds, sample_n, 0, False)
+        crit = SmoothClsLoss()
+        def step():
+            model.zero_grad(set_to_none=True)
+            crit(model(pts), target).backward()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return sample_clouds / dt, dt, cores
+
+
+# -------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("RSB_WORKLOAD", "seg"), choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    wl = WORKLOADS[args.workload]
+    metric = "clouds/sec fwd+bwd RepSurf-U"
+    sample = dict(seg=(1, 40960), cls=(8, 1024))[args.workload]
+
+    # ---------------- reference arm: the CPU port on the host cores (rank 0 only) ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        warm = 1 if args.warmup > 0 else 0
+        v, dt, cores = cpu_port_run(args.workload, steps, warm, *sample)
+        desc = f"{sample[0]} cloud(s) x N={sample[1]} of the same workload, fwd+bwd, {steps} step(s)"
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": "clouds/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"], "sample": desc},
+            "cpu_baseline": {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- our arm ---------------------------------------------------------------------
+    import torch.distributed as dist
+    from repsurf_b200 import _native
+    from repsurf_b200.models import RepSurfCls, RepSurfSeg, SmoothClsLoss
+    from repsurf_b200.seg import pointops as PS
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False          # fp32-faithful MLP (north star: 1e-5 rel)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(rank)
+    np.random.seed(rank)
+
+    model = (RepSurfSeg() if args.workload == "seg" else RepSurfCls()).to(dev).train()
+    crit = nn.CrossEntropyLoss() if args.workload == "seg" else SmoothClsLoss()
+    params = [p for p in model.parameters()]
+    # one flat gradient buffer: backward accumulates straight into it, ONE all-reduce per step (3.9 MB seg / 5.9 MB cls)
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    o = 0
+    for p in params:
+        p.grad = flat[o:o + p.numel()].view_as(p)
+        o += p.numel()
+    if world > 1:
+        for p in params:
+            dist.broadcast(p.data, 0)
+        for b in model.buffers():
+            dist.broadcast(b, 0)
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4)
+
+    host = make_inputs(args.workload, wl["clouds"], wl["n"], 100 + rank, pin=True)
+    devin = [t.to(dev) for t in host]
+    if args.workload == "seg":
+        PS.register_offsets(devin[2], host[2].tolist())
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+
+    def fwd_bwd(inp):
+        flat.zero_()
+        if args.workload == "seg":
+            loss = crit(model([inp[0], inp[1], inp[2]]), inp[3])
+        else:
+            loss = crit(model(inp[0]), inp[1])
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.div_(world)
+        opt.step()
+        return loss
+
+    def step_resident():
+        return fwd_bwd(devin)
+
+    def step_e2e():
+        inp = [t.to(dev, non_blocking=True) for t in host]
+        if args.workload == "seg":
+            PS.register_offsets(inp[2], host[2].tolist())   # the host already holds the offsets it uploads
+        loss = fwd_bwd(inp)
+        return float(loss)                                   # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _native.reset_launch_count()
+    with EntryTimer(_native) as et:
+        ms_step = timed(step_resident, args.steps)
+    launches = _native.launch_count()
+    per_entry = et.summary()
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    clouds_total = wl["clouds"] * world
+    value = clouds_total / (ms_step * 1e-3)
+    e2e_value = clouds_total / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant repsurf_b200 kernel (by time inside the timed region) ----
+    hbm_peak, _tf_peak, peak_src = peaks()
+    dom = max(per_entry.items(), key=lambda kv: kv[1]["ms"]) if per_entry else None
+    roof = None
+    entry_share = {k: round(v["ms"] / (ms_step * args.steps), 4) for k, v in per_entry.items()}
+    fps_names = ("rsb_furthestsampling_packed", "rsb_furthestsampling_dense")
+    fps = [(k, v) for k, v in per_entry.items() if k in fps_names]
+    if fps:
+        # FPS is the HBM-roofline kernel named by BASELINE.json; report its LARGEST launch shape
+        # (seg: sa1's launch; cls: sa1's 1024->512).  Algorithmic bytes from the streaming model.
+        if args.workload == "seg":
+            n, segs = wl["n"], wl["clouds"]
+            # training mode: sa1 is sectorized: 4 sectors/cloud of ~n/4 points -> n/16 samples each
+            alg = segs * 4 * fps_algorithmic_bytes(n / 4, n / 16)
+            note = f"sa1 sectorized FPS launch: {segs*4} segments of ~{n//4} pts -> {n//16} samples"
+        else:
+            alg = wl["clouds"] * fps_algorithmic_bytes(wl["n"], 512)
+            note = f"sa1 FPS launch: {wl['clouds']} clouds {wl['n']} -> 512"
+        k, v = fps[0]
+        big = max(t for _a, t in v["each"])
+        big_avg = float(np.mean([t for _a, t in v["each"] if t > 0.5 * big]))
+        ach = alg / (big_avg * 1e-3) / 1e9
+        roof = {"kernel": "fps_kernel (" + k + ")", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src, "launch_ms": big_avg, "launch": note,
+                "algorithmic_bytes_per_launch": alg}
+
+    out = {
+        "metric": metric, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "clouds_per_gpu": wl["clouds"], "points_per_cloud": wl["n"], "parallelism": f"dp{world}",
+                   "optimizer_step": "SGD momentum inside the timed region", "tf32": False,
+                   "l2": "per-step working set (activations > 126 MB) exceeds L2; no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "roofline": roof, "entry_time_share": entry_share,
+        "dominant_entry": dom[0] if dom else None, "clocks": clk,
+    }
+    if not args.no_cpu_baseline:
+        v, dt, cores = cpu_port_run(args.workload, 1, 0, *sample)
+        out["cpu_baseline"] = {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port",
+                               "sample": f"{sample[0]} cloud(s) x N={sample[1]}, fwd+bwd, 1 step ({dt:.1f} s)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -206,8 +206,9 @@ def sectorized_fps(xyz, offset, new_offset, num_sectors, min_points=10000):
     return indices[idx.long()]
 
 
-def knn_packed(nsample, xyz, new_xyz, offset, new_offset):
-    """seg/po/functions/pointops.py:114-130: returns (idx int32 [m,ns], sqrt(dist2) [m,ns])."""
+def knn_packed(nsample, xyz, new_xyz, offset, new_offset, sqrt=True):
+    """seg/po/functions/pointops.py:114-130: returns (idx int32 [m,ns], sqrt(dist2) [m,ns]); sqrt=False gives the
+    kernel's raw squared distances."""
     if new_xyz is None:
         new_xyz = xyz
     m = new_xyz.shape[0]
@@ -215,7 +216,7 @@ def knn_packed(nsample, xyz, new_xyz, offset, new_offset):
     d2 = torch.zeros(m, nsample, dtype=torch.float32)
     lib().orc_knn_packed(_c_int(m), _c_int(nsample), _p(xyz), _p(new_xyz), _p(offset), _p(new_offset), _p(idx),
                          _p(d2))
-    return idx, torch.sqrt(d2)
+    return idx, (torch.sqrt(d2) if sqrt else d2)
 
 
 def group_packed_fwd(inp, idx):

@@ -223,7 +223,8 @@ struct FpsPlan {
     int cs, nt, ppt;
 };
 
-// Choose (cluster size, threads, points/thread) for the largest segment.
+// Choose (cluster size, threads, points/thread).  `n_max` here is the number of PRIORITY POSITIONS the
+// largest segment spans (BS * ceil(n / BS) >= n: the position space is padded to whole reference threads).
 FpsPlan fps_plan(int n_max)
 {
     FpsPlan pl;
@@ -270,8 +271,12 @@ int fps_launch_ppt(const FpsParams &P, int nseg, const FpsPlan &pl, cudaStream_t
     return 0;
 }
 
-int fps_launch(FpsParams P, int nseg, int n_max, cudaStream_t stream)
+int fps_launch(FpsParams P, int nseg, int n_max_pts, cudaStream_t stream)
 {
+    // positions spanned by the largest segment; with a device-side n_max the reference block size may be
+    // smaller than the host's bound, so allow one extra block of padding
+    int n_max = RSB_DIVUP(n_max_pts, P.bs_ref) * P.bs_ref;
+    if (P.n_max_dev) n_max = n_max_pts + 1024;
     FpsPlan pl = fps_plan(n_max);
     if (const char *e = getenv("RSB_FPS_PLAN")) {  // tuning hook: "cs,nt"
         int cs = 0, nt = 0;

@@ -16,6 +16,9 @@ from torch.autograd import Function
 
 from .. import _native as N
 
+# sectorized FPS: keep the sector sizes on the device (no host sync, larger launch) or read back their maximum
+SECTOR_SIZES_ON_DEVICE = False
+
 # ---------------------------------------------------------------------------------------------
 # host copies of offset tensors
 # ---------------------------------------------------------------------------------------------
@@ -120,11 +123,17 @@ class SectorizedFurthestSampling(Function):
         order = torch.sort(seg_id, stable=True)[1]                             # sector-major, ascending index inside
         counts = torch.bincount(seg_id, minlength=nseg)
         sector_offset = counts.cumsum(0).to(torch.int32)
-        n_max_dev = counts.max().to(torch.int32).reshape(1)
         sector_xyz = xyz[order].contiguous()
         idx = torch.empty(noff[-1], dtype=torch.int32, device=dev)
-        N.call("rsb_furthestsampling_packed", nseg, max(sizes), n_max_dev, sector_xyz, sector_offset,
-               new_sector_offset, None, idx, None)
+        if SECTOR_SIZES_ON_DEVICE:
+            # fully asynchronous: the launch is sized for the whole cloud, the tie rule comes from the device scalar
+            n_max_dev = counts.max().to(torch.int32).reshape(1)
+            N.call("rsb_furthestsampling_packed", nseg, max(sizes), n_max_dev, sector_xyz, sector_offset,
+                   new_sector_offset, None, idx, None)
+        else:
+            # one scalar read-back buys a launch sized for the largest SECTOR (4x fewer register slots per thread)
+            N.call("rsb_furthestsampling_packed", nseg, int(counts.max()), None, sector_xyz, sector_offset,
+                   new_sector_offset, None, idx, None)
         out = order[idx.long()]
         ctx.mark_non_differentiable(out)
         return out
