@@ -118,6 +118,21 @@ int rsb_interpolation_packed_forward(int n, int c, int k, const float *input, co
 int rsb_interpolation_packed_backward(int n, int c, int k, const float *grad_output, const int *idx,
                                       const float *weight, float *grad_input, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ shared MLP on tcgen05 (both layouts)
+ * Replaces the library GEMMs behind nn.Conv2d/Conv1d(1x1)/nn.Linear on the RepSurf path
+ * (classification/modules/repsurface_utils.py:236-243, segmentation/modules/repsurface_utils.py:220-227,267-282)
+ * with a 3xTF32 (fp32-faithful) tensor-core GEMM over rows that fuses the PREVIOUS layer's BatchNorm+ReLU into
+ * the operand load and THIS layer's BatchNorm statistics into the epilogue.
+ *   Y[rows,N] = act(X)[rows,K] @ W[N,K]^T + bias
+ *   mode 0: act = identity; 1: relu(x*sc+sh) with sc/sh [K]; 2: relu(x[:, :K]*sc[:K]+sh[:K] + x[:, K:2K]*sc[K:]+sh[K:])
+ *   stats: optional fp64 [2N] (caller-zeroed): += per-column sum and sum of squares of Y.
+ * Weights are pre-split (hi/lo tf32) into the tensor-core operand layout once per step by rsb_linear_tc_prep_weight
+ * into a buffer of rsb_linear_tc_weight_floats(N, K) floats; transposed != 0 takes W stored as [K, N]. */
+long rsb_linear_tc_weight_floats(int N, int K);
+int rsb_linear_tc_prep_weight(int N, int K, const float *W, int ldw, int transposed, float *Wp, cudaStream_t stream);
+int rsb_linear_tc_forward(long rows, int K, int N, const float *X, int ldx, const float *Wp, const float *bias,
+                          int mode, const float *sc, const float *sh, float *Y, double *stats, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ _lib = None
 _i = ctypes.c_int
 _f = ctypes.c_float
 _p = ctypes.c_void_p
+_l = ctypes.c_long
 
 # name -> argtypes (the trailing cudaStream_t is appended automatically)
 _SIGS = {
@@ -37,8 +38,11 @@ _SIGS = {
     "rsb_grouping_packed_backward": [_i, _i, _i, _p, _p, _p],
     "rsb_interpolation_packed_forward": [_i, _i, _i, _p, _p, _p, _p],
     "rsb_interpolation_packed_backward": [_i, _i, _i, _p, _p, _p, _p],
+    "rsb_linear_tc_prep_weight": [_i, _i, _p, _i, _i, _p],
+    "rsb_linear_tc_forward": [_l, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p],
 }
-EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
+                                "rsb_linear_tc_weight_floats"])
 
 
 def build(force=False):
@@ -65,6 +69,8 @@ def lib():
         L.rsb_last_error.restype = ctypes.c_char_p
         L.rsb_launch_count.restype = ctypes.c_ulonglong
         L.rsb_abi_version.restype = _i
+        L.rsb_linear_tc_weight_floats.restype = _l
+        L.rsb_linear_tc_weight_floats.argtypes = [_i, _i]
         _lib = L
     return _lib
 

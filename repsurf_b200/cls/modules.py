@@ -18,43 +18,49 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointops as P
+from ..seg import pointops as PP
 from ..geometry import umbrella_features, xyz2sphere
+from ..mlp import bn_rows, linear_rows, sa_mlp_rows
 
 
 def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_normal, return_polar):
-    """Sampling + ball-query grouping (reference sample_and_group, repsurface_utils.py:15-59), channel-first.
+    """Sampling + ball-query grouping (reference sample_and_group, repsurface_utils.py:15-59).
     center_cf [B,3,N], normal [B,Cn,N], feature [B,Cf,N]|None ->
-      new_center [B,3,m], new_normal [B,Cn,m], grouped [B, C, m, ns] with C ordered
-      [rel xyz(3), polar(3)?, normal(Cn)?, feature(Cf)?]."""
-    center_cf = center_cf.contiguous()
-    xyz = center_cf.transpose(1, 2).contiguous()                       # [B,N,3] for the query kernels
+      new_center [B,3,m], new_normal [B,Cn,m], rows [B*m*ns, C] with C ordered
+      [rel xyz(3), polar(3)?, normal(Cn)?, feature(Cf)?].
+    Groups are gathered ROW-major (one contiguous C-vector per (centre, sample)) with the packed grouping
+    kernel on a [B*N, C] view and globalised indices, so the shared MLP runs as plain GEMMs over rows."""
+    B, _, N = center_cf.shape
+    xyz = center_cf.transpose(1, 2).contiguous()                       # [B,N,3]
     fps_idx, new_xyz = P.furthestsampling_with_xyz(xyz, npoint)         # [B,m], [B,m,3]
     new_normal = P.gathering(normal.contiguous(), fps_idx)              # [B,Cn,m]
-    idx = P.ballquery(radius, nsample, xyz, new_xyz)                    # [B,m,ns]
-    new_center = new_xyz.transpose(1, 2).contiguous()                   # [B,3,m]
-    rel = P.grouping(center_cf, idx) - new_center.unsqueeze(-1)         # [B,3,m,ns]
+    idx = P.ballquery(radius, nsample, xyz, new_xyz)                    # [B,m,ns] local ids
+    gidx = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N).view(B, 1, 1)).view(B * npoint, nsample)
+    rel = PP.grouping(xyz.view(B * N, 3), gidx) - new_xyz.view(B * npoint, 1, 3)       # [B*m,ns,3]
     parts = [rel]
     if return_polar:
-        parts.append(xyz2sphere(rel.permute(0, 2, 3, 1)).permute(0, 3, 1, 2))
+        parts.append(xyz2sphere(rel))
     if feature is None or return_normal:
-        parts.append(P.grouping(normal.contiguous(), idx))
+        parts.append(PP.grouping(normal.transpose(1, 2).reshape(B * N, -1), gidx))
     if feature is not None:
-        parts.append(P.grouping(feature.contiguous(), idx))
-    return new_center, new_normal, torch.cat(parts, dim=1)
+        parts.append(PP.grouping(feature.transpose(1, 2).reshape(B * N, -1), gidx))
+    rows = torch.cat(parts, dim=-1)
+    return new_xyz.transpose(1, 2).contiguous(), new_normal, rows.view(B * npoint * nsample, -1)
 
 
 def _all_inputs(center_cf, normal, feature, return_normal, return_polar):
     """group_all (reference sample_and_group_all, repsurface_utils.py:62-88): one group holding every point,
-    RAW coordinates (not centre-relative), new_center = new_normal = zeros[B,3,1]."""
-    B = center_cf.shape[0]
+    RAW coordinates (not centre-relative), new_center = new_normal = zeros[B,3,1].  -> rows [B*N, C]."""
+    B, _, N = center_cf.shape
     new_center = torch.zeros(B, 3, 1, device=center_cf.device, dtype=center_cf.dtype)
-    parts = [center_cf]
+    xyz = center_cf.transpose(1, 2)
+    parts = [xyz]
     if return_polar:
-        parts.append(xyz2sphere(center_cf.transpose(1, 2)).transpose(1, 2))
+        parts.append(xyz2sphere(xyz))
     if return_normal:
-        parts.append(normal)
-    parts.append(feature)
-    return new_center, new_center, torch.cat(parts, dim=1).unsqueeze(2)  # [B,C,1,N]
+        parts.append(normal.transpose(1, 2))
+    parts.append(feature.transpose(1, 2))
+    return new_center, new_center, torch.cat(parts, dim=-1).reshape(B * N, -1)
 
 
 class SurfaceAbstractionCD(nn.Module):
@@ -81,16 +87,17 @@ class SurfaceAbstractionCD(nn.Module):
             last = out_channel
 
     def forward(self, center, normal, feature):
+        B, N = center.shape[0], center.shape[2]
         if self.group_all:
-            new_center, new_normal, x = _all_inputs(center, normal, feature, self.return_normal, self.return_polar)
+            new_center, new_normal, rows = _all_inputs(center, normal, feature, self.return_normal, self.return_polar)
+            groups, ns = 1, N
         else:
-            new_center, new_normal, x = _grouped_inputs(self.npoint, self.radius, self.nsample, center, normal,
-                                                        feature, self.return_normal, self.return_polar)
+            new_center, new_normal, rows = _grouped_inputs(self.npoint, self.radius, self.nsample, center, normal,
+                                                           feature, self.return_normal, self.return_polar)
+            groups, ns = self.npoint, self.nsample
         # channel de-differentiation: position and feature channels get their own first layer (:236-239)
-        x = F.relu(self.bn_l0(self.mlp_l0(x[:, :self.pos_channel])) + self.bn_f0(self.mlp_f0(x[:, self.pos_channel:])))
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            x = F.relu(bn(conv(x)))
-        return new_center, new_normal, torch.max(x, 3)[0]
+        pooled = sa_mlp_rows(rows, self.pos_channel, self, ns)                # [B*groups, C']
+        return new_center, new_normal, pooled.view(B, groups, -1).transpose(1, 2).contiguous()
 
 
 class UmbrellaSurfaceConstructor(nn.Module):
@@ -126,10 +133,15 @@ class UmbrellaSurfaceConstructor(nn.Module):
             feat = umbrella_features(offsets, flip, rotate_key=False, order="cls")   # [B,N,G,10]
             if not self.return_dist:
                 feat = feat[..., :9]
-            x = feat.permute(0, 3, 1, 2).contiguous()                           # [B,C,N,G]
-        x = self.mlps(x)
+            G, C = feat.shape[2], feat.shape[3]
+            rows = feat.reshape(B * N * G, C)
+        x = F.relu(bn_rows(linear_rows(rows, self.mlps[0]), self.mlps[1]))
+        x = F.relu(bn_rows(linear_rows(x, self.mlps[3]), self.mlps[4]))
+        x = linear_rows(x, self.mlps[6]).view(B, N, G, -1)
         if self.aggr_type == 'max':
-            return torch.max(x, 3)[0]
-        if self.aggr_type == 'avg':
-            return torch.mean(x, 3)
-        return torch.sum(x, 3)
+            x = torch.max(x, 2)[0]
+        elif self.aggr_type == 'avg':
+            x = torch.mean(x, 2)
+        else:
+            x = torch.sum(x, 2)
+        return x.transpose(1, 2).contiguous()

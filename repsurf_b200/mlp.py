@@ -1,0 +1,37 @@
+"""Shared-MLP evaluation on ROW MATRICES [rows, C] (rows = every (centre, sample) pair of a level).
+
+The reference evaluates the per-group MLP as 1x1 Conv2d/Conv1d + BatchNorm2d/1d over [B,C,ns,m] / [M,C,ns]
+(classification/modules/repsurface_utils.py:233-244, segmentation/modules/repsurface_utils.py:217-228), which
+sends cuDNN down its worst paths on a B200 (grouped-direct wgrad, 1C11 batch-norm: 77 % of a step, see
+profiles/r01_torch_profile_seg_v1.txt).  A 1x1 convolution over that layout IS a GEMM over rows, and
+BatchNorm over (B, ns, m) per channel IS BatchNorm over rows, so everything here works on [rows, C] with the
+parameters of the reference's layer objects (weights [out,in,1(,1)] viewed as [out,in]).
+
+This module is the seam where the fused sm_100a kernels plug in (gather -> GEMM -> BN statistics epilogue).
+"""
+import torch
+import torch.nn.functional as F
+
+
+def linear_rows(x, layer):
+    w = layer.weight
+    return F.linear(x, w.view(w.shape[0], -1), layer.bias)
+
+
+def bn_rows(x, bn):
+    """Train/eval BatchNorm over rows with the module's buffers (same side effects as calling the module)."""
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    use_batch = bn.training or bn.running_mean is None
+    return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, use_batch,
+                        0.0 if bn.momentum is None else bn.momentum, bn.eps)
+
+
+def sa_mlp_rows(rows, pos_channel, mod, nsample):
+    """Channel-de-differentiated shared MLP + max-pool.  rows [G*nsample, C] -> [G, mlp[-1]].
+    mod provides mlp_l0/mlp_f0/bn_l0/bn_f0/mlp_convs/mlp_bns (the reference's attribute names)."""
+    x = F.relu(bn_rows(linear_rows(rows[:, :pos_channel], mod.mlp_l0), mod.bn_l0)
+               + bn_rows(linear_rows(rows[:, pos_channel:], mod.mlp_f0), mod.bn_f0))
+    for lin, bn in zip(mod.mlp_convs, mod.mlp_bns):
+        x = F.relu(bn_rows(linear_rows(x, lin), bn))
+    return x.view(-1, nsample, x.shape[-1]).max(dim=1)[0]

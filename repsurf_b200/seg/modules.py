@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 from . import pointops as P
 from ..geometry import umbrella_features, xyz2sphere
+from ..mlp import bn_rows, linear_rows, sa_mlp_rows
 
 
 def strided_offsets(offset, stride):
@@ -85,11 +86,8 @@ class SurfaceAbstractionCD(nn.Module):
         new_center, new_normal, x, new_offset = _sample_and_group(
             self.stride, self.nsample, center, normal, feature, offset, self.return_polar, self.num_sector,
             self.training)
-        x = x.transpose(1, 2).contiguous()                                  # [M,C,ns]
-        x = F.relu(self.bn_l0(self.mlp_l0(x[:, :self.pos_channel])) + self.bn_f0(self.mlp_f0(x[:, self.pos_channel:])))
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            x = F.relu(bn(conv(x)))
-        return [new_center, new_normal, torch.max(x, 2)[0], new_offset]
+        M, ns, C = x.shape
+        return [new_center, new_normal, sa_mlp_rows(x.view(M * ns, C), self.pos_channel, self, ns), new_offset]
 
 
 class SurfaceFeaturePropagationCD(nn.Module):
@@ -158,5 +156,7 @@ class UmbrellaSurfaceConstructor(nn.Module):
             else:
                 flip = torch.ones(1, 1, 1, device=center.device)
             feat = umbrella_features(offsets, flip, rotate_key=(self.sort == 'fix'), order="seg")  # [N,k,10]
-            x = feat.transpose(1, 2).contiguous()                            # [N,10,k]
-        return torch.sum(self.mlps(x), 2)
+            n, g, c = feat.shape
+            rows = feat.reshape(n * g, c)
+        x = F.relu(bn_rows(linear_rows(rows, self.mlps[0]), self.mlps[1]))
+        return linear_rows(x, self.mlps[3]).view(n, g, -1).sum(dim=1)
