@@ -133,6 +133,66 @@ int rsb_linear_tc_prep_weight(int N, int K, const float *W, int ldw, int transpo
 int rsb_linear_tc_forward(long rows, int K, int N, const float *X, int ldx, const float *Wp, const float *bias,
                           int mode, const float *sc, const float *sh, float *Y, double *stats, cudaStream_t stream);
 
+/* General form used by the fused shared-MLP forward/backward.  An OPERAND is a logical [rows, K] matrix whose
+ * element (r, k) is computed from stored tensors while the tile is staged (k below already includes k0): */
+enum {
+    RSB_OPND_RAW = 0,           /* U[r,k]                                                                     */
+    RSB_OPND_BN_RELU = 1,       /* relu(a[k]*U[r,k] + d[k])                      previous BatchNorm + ReLU       */
+    RSB_OPND_DUAL_BN_RELU = 2,  /* relu(a[k]*U[r,k]+d[k] + a[ku+k]*U[r,ku+k]+d[ku+k])   relu(bn_l(y_l)+bn_f(y_f)) */
+    RSB_OPND_AFFINE2 = 3,       /* a[k]*U[r, k % ku] + b[k]*V[r,k] + d[k]        BatchNorm backward dY            */
+    RSB_OPND_POOLED = 4         /* a[k]*(arg[g,k]==r-g*ns ? U[g,k] : 0) + b[k]*V[r,k] + d[k],  g = r / ns        */
+};
+typedef struct {
+    const float *U, *V;      /* U: [rows, ldu] (POOLED: [rows/ns, ldu] pooled gradient), V: [rows, ldv]            */
+    const float *a, *b, *d;  /* per-channel coefficients                                                          */
+    const int *arg;          /* POOLED: [rows/ns, ldu] sample index of the pooled maximum                         */
+    int ldu, ldv;
+    int K;                   /* logical width of the operand                                                      */
+    int k0;                  /* channel offset added to every k                                                   */
+    int ku;                  /* DUAL: half width; AFFINE2: width of U (k % ku)                                    */
+    int kind, ns;
+} rsb_opnd_t;
+
+enum {
+    RSB_EPI_BIAS_STATS = 0,  /* y = acc + bias[n]; stats[2N] += (sum y, sum y^2)                                  */
+    RSB_EPI_RELU_MASK = 1    /* y = z > 0 ? acc : 0 with z = sc[n]*Yl[r,n]+sh[n] (+ dual: second half at N+n);
+                                stats[2N or 3N] += (sum y, sum y*xhat1 [, sum y*xhat2]), xhat = (Yl-mu)*inv      */
+};
+typedef struct {
+    float *Y;                /* [rows, ldy] or NULL                                                               */
+    int ldy;
+    const float *bias;       /* BIAS_STATS, may be NULL                                                           */
+    double *stats;           /* caller-zeroed, may be NULL                                                        */
+    const float *Yl;         /* RELU_MASK: stored pre-BatchNorm output of the layer below, [rows, ldl]             */
+    int ldl;
+    const float *sc, *sh, *mu, *inv;
+    int kind, dual;
+} rsb_epi_t;
+
+/* Y = A @ W^T with W pre-split by rsb_linear_tc_prep_weight(N, A->K, ...). */
+int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float *Wp, const rsb_epi_t *E, cudaStream_t stream);
+/* dW[m, n] += sum_r G(r, m) * X(r, n);  dW is [G->K, ldw] fp32, accumulated with atomics (caller zeroes it). */
+int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, float *dW, int ldw, cudaStream_t stream);
+
+/* Per-channel helpers of the fused shared MLP (train-mode BatchNorm, max-pool over nsample):
+ * rsb_bn_finalize: stats (sum, sum^2 over `rows`) -> sc = gamma/sqrt(var+eps), sh = beta - mean*sc, mu, inv; updates
+ *   running_mean/var in place when given (torch semantics: biased variance to normalise, unbiased for the running value).
+ * rsb_pool_forward: out[g,c] = max_s relu(sc*Y[g*ns+s,c]+sh), arg = first maximising s.
+ * rsb_pool_backward_stats: dm = dOut masked by (pooled value > 0); stats[2C] += (sum dm, sum dm*xhat at the arg-max row).
+ * rsb_bn_backward_coef: coefficients of dY = a*dZ + b*Y + d (BatchNorm backward) + dgamma/dbeta, from
+ *   stats = (sum dZ, sum dZ*xhat [, second xhat when dual]). */
+int rsb_bn_finalize(int C, long rows, const double *stats, const float *gamma, const float *beta, float eps,
+                    float momentum, float *running_mean, float *running_var, float *sc, float *sh, float *mu,
+                    float *inv, cudaStream_t stream);
+int rsb_pool_forward(long G, int ns, int C, const float *Y, int ldy, const float *sc, const float *sh, float *out,
+                     int *arg, cudaStream_t stream);
+int rsb_pool_backward_stats(long G, int ns, int C, const float *dOut, const int *arg, const float *Y, int ldy,
+                            const float *sc, const float *sh, const float *mu, const float *inv, float *dm,
+                            double *stats, cudaStream_t stream);
+int rsb_bn_backward_coef(int C, long rows, const double *stats, int dual, const float *sc, const float *mu,
+                         const float *inv, float *a, float *b, float *d, float *dgamma, float *dbeta,
+                         cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,12 @@ _SIGS = {
     "rsb_interpolation_packed_backward": [_i, _i, _i, _p, _p, _p, _p],
     "rsb_linear_tc_prep_weight": [_i, _i, _p, _i, _i, _p],
     "rsb_linear_tc_forward": [_l, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p],
+    "rsb_gemm_rows": [_l, _i, _p, _p, _p],
+    "rsb_gemm_wgrad": [_l, _p, _p, _p, _i],
+    "rsb_bn_finalize": [_i, _l, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p],
+    "rsb_pool_forward": [_l, _i, _i, _p, _i, _p, _p, _p, _p],
+    "rsb_pool_backward_stats": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
+    "rsb_bn_backward_coef": [_i, _l, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
                                 "rsb_linear_tc_weight_floats"])
@@ -88,7 +94,7 @@ def _ptr(t):
 def call(name, *args):
     """Invoke a C-ABI entry on torch's current stream; tensors are passed as device pointers."""
     L = lib()
-    conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else (ctypes.addressof(a) if isinstance(a, ctypes.Structure) else a)) for a in args]
     stream = torch.cuda.current_stream().cuda_stream
     rc = getattr(L, name)(*conv, stream)
     if rc != 0:

@@ -1,50 +1,60 @@
-// mlp_tc.cu — the shared-MLP GEMM of RepSurf-U on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-faithful.
+// mlp_tc.cu — the shared-MLP GEMMs of RepSurf-U on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-faithful.
 //
-//   Y[r, n] = sum_k act(X)[r, k] * W[n, k] + bias[n]            rows x K  @  (N x K)^T
+// Two kernels cover forward, input-gradient and weight-gradient of every 1x1-conv / linear layer on the path:
 //
-// replaces the reference's library calls nn.Conv2d/Conv1d(1x1)/nn.Linear on the RepSurf path
+//   gemm_rows_kernel :  Y[r, n]  = sum_k A(r, k) * W[n, k]        (rows x K) @ (N x K)^T     forward + dgrad
+//   gemm_wgrad_kernel:  dW[m, n] += sum_r G(r, m) * X(r, n)       (rows x M)^T @ (rows x N)  wgrad (operands
+//                       transposed into K-major tiles while they are staged)
+//
+// They replace the reference's library calls nn.Conv2d/Conv1d(1x1)/nn.Linear (+ autograd) on the RepSurf path
 //   classification/modules/repsurface_utils.py:236-243, segmentation/modules/repsurface_utils.py:220-227, 267-282
-// and FUSES what the reference runs as separate cuDNN / elementwise passes around them:
-//   * prologue  act(X): the previous layer's train-mode BatchNorm + ReLU is applied while the A tile is
-//     staged (per-channel scale/shift), including the channel-de-differentiated first layer
-//     relu(bn_l(y_l) + bn_f(y_f)) ("dual" mode) — the normalised activations never exist in HBM;
-//   * epilogue: + bias, store Y once, and the per-channel sum / sum-of-squares needed by THIS layer's
-//     BatchNorm statistics, accumulated in fp64.
+// and FUSE what the reference runs as separate cuDNN / elementwise passes around them.  Operands are never
+// materialised in HBM in their "activated" form: A(r,k), G(r,m), X(r,n) are computed while the tile is staged
+// (`Opnd`): train-mode BatchNorm + ReLU of the previous layer, the channel-de-differentiated first layer
+// relu(bn_l(y_l) + bn_f(y_f)), the BatchNorm-backward affine dY = a*dZ + b*Y + d, and the max-pool backward
+// selection.  Epilogues (`Epi`) add the bias, apply the ReLU mask of the layer below (dgrad) and accumulate the
+// per-channel statistics the NEXT BatchNorm step needs (forward: sum, sum^2; backward: sum dZ, sum dZ*xhat) in fp64.
 //
 // Numerics: tcgen05 has no fp32 x fp32 MMA.  Every operand is split a = hi + lo with hi = tf32(a),
-// lo = tf32(a - hi) and three kind::tf32 MMAs (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM
-// ("3xTF32"): ~2^-21 relative per product, i.e. fp32-level, which the 1e-5 parity bar needs (plain TF32
-// gives 1e-3).  The dropped lo*lo term is < 2^-22.
+// lo = tf32(a - hi); three kind::tf32 MMAs (lo*hi + hi*lo + hi*hi) accumulate in fp32 in TMEM ("3xTF32"):
+// ~2^-21 relative per product, i.e. fp32-level, which the 1e-5 parity bar needs (plain TF32 gives 1e-3).
 //
-// Structure (one CTA per SM, persistent over 128-row tiles; 9 warps):
-//   warps 0-3  producers: one thread per row; load K-chunk (32) of X, apply act(), split hi/lo, write both
-//              tiles to shared memory in the UMMA canonical K-major no-swizzle layout (8x16B core matrices);
-//              one elected thread also fetches the matching pre-split weight chunk with cp.async.bulk (TMA 1D).
-//   warp  4    MMA issuer: one elected lane issues 4 k-steps x 3 tcgen05.mma per chunk into a double-buffered
-//              TMEM accumulator (128 lanes x N columns), tcgen05.commit -> mbarriers.
-//   warps 5-8  epilogue: tcgen05.ld 32x32b -> registers -> +bias -> global store + fp64 column statistics.
+// Structure of both kernels (one persistent CTA per SM, 9 warps):
+//   warps 0-3  producers: evaluate the operand transform, split hi/lo, write both tiles to shared memory in the
+//              UMMA canonical no-swizzle layout (8 x 16 B core matrices); gemm_rows also fetches the matching
+//              pre-split weight chunk with cp.async.bulk (TMA 1-D) onto the same mbarrier.
+//   warp  4    MMA issuer: one elected lane issues 4 k-steps x 3 tcgen05.mma per 32-deep chunk into a
+//              double-buffered TMEM accumulator (128 lanes x <=256 columns), tcgen05.commit -> mbarriers.
+//   warps 5-8  epilogue: tcgen05.ld 32x32b -> registers -> epilogue transform -> global (+ fp64 statistics).
 #include "common.cuh"
+#include "mlp_tc.h"
 
 namespace {
 
-constexpr int TM = 128;          // rows per tile (UMMA M)
-constexpr int KC = 32;           // K elements per pipeline chunk (4 UMMA k-steps of 8)
+constexpr int TM = 128;          // UMMA M
+constexpr int KC = 32;           // reduction elements per pipeline chunk (4 UMMA k-steps of 8)
 constexpr int STAGES = 2;
-constexpr int NT_MAX = 256;      // columns per N tile (UMMA N <= 256)
-constexpr int A_TILE_BYTES = TM * KC * 4;           // 16 KB (one of hi / lo)
+constexpr int NT_MAX = 256;      // UMMA N <= 256
+constexpr int A_TILE_BYTES = TM * KC * 4;           // 16 KB (one of hi / lo), K-major tiles
 constexpr int THREADS = 9 * 32;
 
-struct TcParams {
-    const float *X;      // [rows, ldx]
-    const float *Wp;     // pre-split weights, canonical layout: [n_tiles][k_chunks][2 (hi,lo)][NT x KC]
-    const float *bias;   // [N] or nullptr
-    const float *sc;     // prologue scale  [K] (mode 1) or [2K] (mode 2)
-    const float *sh;     // prologue shift
-    float *Y;            // [rows, N]
-    double *stats;       // [2N]: sum, sum of squares (accumulated with atomics) or nullptr
+typedef rsb_opnd_t Opnd;
+typedef rsb_epi_t Epi;
+
+struct RowsParams {
+    Opnd A;
+    Epi E;
+    const float *Wp;
     long rows;
-    int K, ldx, N, NT, n_tiles, k_chunks;
-    int mode;            // 0: A = X;  1: A = relu(X*sc+sh);  2: A = relu(X[:, :K]*sc+sh + X[:, K:2K]*sc'+sh')
+    int N, NT, n_tiles, k_chunks;
+};
+
+struct WgradParams {
+    Opnd G, X;
+    float *dW;
+    int ldw;
+    long rows;
+    int M, N, NT, m_tiles, n_tiles;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -76,10 +86,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -91,9 +98,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-// UMMA shared-memory descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-//   [0,14) start>>4, [16,30) leading-dim byte offset>>4 (between core matrices along K),
-//   [32,46) stride-dim byte offset>>4 (between 8-row groups), [46,48) version = 1, [61,64) layout = 0.
+// UMMA shared-memory descriptor, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4, [16,30) leading-dim byte offset>>4, [32,46) stride-dim byte offset>>4, [46,48) version = 1,
+//   [61,64) layout = 0 (INTERLEAVE).  K-major:  LBO = between core matrices along K, SBO = between 8-row groups.
+//   MN-major: LBO = between 8-deep groups along K, SBO = between 4-channel groups along MN.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
 {
     uint64_t d = 0;
@@ -104,11 +112,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, 
     return d;
 }
 
-// instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major (InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
+// instruction descriptor, kind::tf32, fp32 accumulate (InstrDescriptor bit layout); mn_major sets both operands
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool mn_major)
 {
     return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+           (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -150,113 +158,159 @@ __device__ __forceinline__ float to_tf32(float x)
     return __uint_as_float(r);
 }
 
-// shared-memory carve-up
-struct Smem {
-    // stage s: A_hi, A_lo (16 KB each), B_hi, B_lo (NT*128 B each)
-    static __device__ __forceinline__ size_t stage_bytes(int NT) { return 2 * A_TILE_BYTES + 2 * (size_t)NT * KC * 4; }
+// ---- operand transform ------------------------------------------------------------------------------------
+// value of logical element (row r, channel k) of an operand; k already includes O.k0; caller guarantees r < rows.
+__device__ __forceinline__ float opnd_load(const Opnd &O, long r, int k)
+{
+    switch (O.kind) {
+    case RSB_OPND_RAW:
+        return __ldg(O.U + (size_t)r * O.ldu + k);
+    case RSB_OPND_BN_RELU:
+        return fmaxf(fmaf(__ldg(O.U + (size_t)r * O.ldu + k), __ldg(O.a + k), __ldg(O.d + k)), 0.f);
+    case RSB_OPND_DUAL_BN_RELU: {
+        const float *u = O.U + (size_t)r * O.ldu;
+        const float z = fmaf(__ldg(u + k), __ldg(O.a + k), __ldg(O.d + k)) +
+                        fmaf(__ldg(u + O.ku + k), __ldg(O.a + O.ku + k), __ldg(O.d + O.ku + k));
+        return fmaxf(z, 0.f);
+    }
+    case RSB_OPND_AFFINE2: {
+        const int ku = k % O.ku;
+        return fmaf(__ldg(O.a + k), __ldg(O.U + (size_t)r * O.ldu + ku),
+                    fmaf(__ldg(O.b + k), __ldg(O.V + (size_t)r * O.ldv + k), __ldg(O.d + k)));
+    }
+    default: {  // RSB_OPND_POOLED: dZ is nonzero only on the arg-max row of its (group, channel)
+        const long g = r / O.ns;
+        const float dz = (__ldg(O.arg + (size_t)g * O.ldu + k) == (int)(r - g * O.ns)) ? __ldg(O.U + (size_t)g * O.ldu + k) : 0.f;
+        return fmaf(__ldg(O.a + k), dz, fmaf(__ldg(O.b + k), __ldg(O.V + (size_t)r * O.ldv + k), __ldg(O.d + k)));
+    }
+    }
+}
+
+__device__ __forceinline__ void split4(const float *v, float4 &hi, float4 &lo)
+{
+    hi.x = to_tf32(v[0]); hi.y = to_tf32(v[1]); hi.z = to_tf32(v[2]); hi.w = to_tf32(v[3]);
+    lo.x = to_tf32(v[0] - hi.x); lo.y = to_tf32(v[1] - hi.y); lo.z = to_tf32(v[2] - hi.z); lo.w = to_tf32(v[3] - hi.w);
+}
+
+// column sums of a warp's 32x32 register tile through a padded shared tile; result for column `lane`
+__device__ __forceinline__ float warp_colsum(float *tile, const float *v, int lane)
+{
+#pragma unroll
+    for (int j = 0; j < 32; j++) tile[lane * 33 + j] = v[j];
+    __syncwarp();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) s += tile[i * 33 + lane];
+    __syncwarp();
+    return s;
+}
+
+struct Barriers {
+    uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+    uint32_t tmem_slot, pad;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(TcParams P)
+__device__ __forceinline__ uint32_t cta_prologue(Barriers *B, int tid, int warp)
 {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int NT = P.NT;
-    const size_t stage_bytes = Smem::stage_bytes(NT);
-    const size_t b_bytes = (size_t)NT * KC * 4;  // one of hi / lo
-    unsigned char *stage_base = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * stage_bytes);
-    uint64_t *full_bar = bars;                 // [STAGES]  producers (128 arrivals + expect_tx thread) -> MMA
-    uint64_t *empty_bar = bars + STAGES;       // [STAGES]  MMA commit -> producers
-    uint64_t *acc_full = bars + 2 * STAGES;    // [2]       MMA commit -> epilogue
-    uint64_t *acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue (128 arrivals) -> MMA
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
-    float *stat_tile = reinterpret_cast<float *>(bars + 2 * STAGES + 6);  // [4 warps][32][33]
-
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 128 + 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&B->full[s], 128 + 1); mbar_init(&B->empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&B->acc_full[a], 1); mbar_init(&B->acc_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(rsb_smem_addr(tmem_slot)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(rsb_smem_addr(&B->tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    return B->tmem_slot;
+}
+
+__device__ __forceinline__ void cta_epilogue(uint32_t tmem_base, int warp)
+{
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+// ============================================================================================================
+// Y = A @ W^T  (forward and input-gradient)
+// ============================================================================================================
+__global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_constant__ RowsParams P)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NT = P.NT;
+    const size_t b_bytes = (size_t)NT * KC * 4;  // one of hi / lo
+    const size_t stage_bytes = 2 * A_TILE_BYTES + 2 * b_bytes;
+    Barriers *B = reinterpret_cast<Barriers *>(smem + STAGES * stage_bytes);
+    float *stat_tile = reinterpret_cast<float *>(B + 1);  // [4 warps][32][33]
+    const uint32_t tmem_base = cta_prologue(B, tid, warp);
 
     const long n_row_tiles = (P.rows + TM - 1) / TM;
     const int kc_count = P.k_chunks;
+    const Opnd &A = P.A;
+    const Epi &E = P.E;
 
     if (warp < 4) {
-        // =============================== producers ===============================
-        const int r = tid;  // row inside the tile
-        uint32_t it = 0;    // global chunk counter -> stage / phase
+        // =============================== producers: one thread per row ===============================
+        const int r = tid;
+        uint32_t it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
             const long row = tile * TM + r;
             const bool row_ok = row < P.rows;
-            const float *xrow = P.X + (size_t)(row_ok ? row : 0) * P.ldx;
             for (int nt = 0; nt < P.n_tiles; nt++) {
                 for (int kc = 0; kc < kc_count; kc++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    unsigned char *st = stage_base + (size_t)s * stage_bytes;
+                    mbar_wait(&B->empty[s], ph ^ 1);
+                    unsigned char *st = smem + (size_t)s * stage_bytes;
                     if (tid == 0) {
-                        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * b_bytes));
+                        mbar_arrive_expect_tx(&B->full[s], (uint32_t)(2 * b_bytes));
                         const float *src = P.Wp + ((size_t)nt * kc_count + kc) * (2 * (size_t)NT * KC);
-                        bulk_g2s(st + 2 * A_TILE_BYTES, src, (uint32_t)(2 * b_bytes), &full_bar[s]);
+                        bulk_g2s(st + 2 * A_TILE_BYTES, src, (uint32_t)(2 * b_bytes), &B->full[s]);
                     }
                     float *a_hi = reinterpret_cast<float *>(st);
                     float *a_lo = reinterpret_cast<float *>(st + A_TILE_BYTES);
-                    const int row_off = (r >> 3) * (KC / 4) * 32 + (r & 7) * 4;  // in floats: (r/8)*SBO + (r%8)*16B
+                    const int row_off = (r >> 3) * (KC / 4) * 32 + (r & 7) * 4;  // floats: (r/8)*SBO + (r%8)*16 B
 #pragma unroll
                     for (int c4 = 0; c4 < KC / 4; c4++) {
                         float v[4];
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const int k = kc * KC + c4 * 4 + e;
-                            float x = 0.f;
-                            if (row_ok && k < P.K) {
-                                x = __ldg(xrow + k);
-                                if (P.mode >= 1) {
-                                    x = fmaf(x, __ldg(P.sc + k), __ldg(P.sh + k));
-                                    if (P.mode == 2) x += fmaf(__ldg(xrow + P.K + k), __ldg(P.sc + P.K + k), __ldg(P.sh + P.K + k));
-                                    x = fmaxf(x, 0.f);
-                                }
-                            }
-                            v[e] = x;
+                            v[e] = (row_ok && k < A.K) ? opnd_load(A, row, A.k0 + k) : 0.f;
                         }
                         float4 hi, lo;
-                        hi.x = to_tf32(v[0]); hi.y = to_tf32(v[1]); hi.z = to_tf32(v[2]); hi.w = to_tf32(v[3]);
-                        lo.x = to_tf32(v[0] - hi.x); lo.y = to_tf32(v[1] - hi.y); lo.z = to_tf32(v[2] - hi.z); lo.w = to_tf32(v[3] - hi.w);
+                        split4(v, hi, lo);
                         *reinterpret_cast<float4 *>(a_hi + row_off + c4 * 32) = hi;
                         *reinterpret_cast<float4 *>(a_lo + row_off + c4 * 32) = lo;
                     }
                     fence_proxy_async();
-                    mbar_arrive(&full_bar[s]);
+                    mbar_arrive(&B->full[s]);
                 }
             }
         }
     } else if (warp == 4) {
         // =============================== MMA issuer ===============================
-        const uint32_t idesc = umma_idesc_tf32(TM, NT);
+        const uint32_t idesc = umma_idesc_tf32(TM, NT, false);
         uint32_t it = 0, acc_it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
             for (int nt = 0; nt < P.n_tiles; nt++, acc_it++) {
                 const int ab = acc_it & 1;
-                const uint32_t aph = (acc_it >> 1) & 1;
-                mbar_wait(&acc_empty[ab], aph ^ 1);
+                mbar_wait(&B->acc_empty[ab], ((acc_it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(ab * NT_MAX);
                 for (int kc = 0; kc < kc_count; kc++, it++) {
                     const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait(&B->full[s], (it / STAGES) & 1);
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t st = rsb_smem_addr(stage_base + (size_t)s * stage_bytes);
+                        const uint32_t st = rsb_smem_addr(smem + (size_t)s * stage_bytes);
                         const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
                         const uint32_t b_hi = st + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)b_bytes;
                         const uint32_t SBO = (KC / 4) * 128, LBO = 128;
@@ -269,8 +323,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(TcParams P)
                             umma_tf32(tmem_d, dah, dbl, idesc, 1u);
                             umma_tf32(tmem_d, dah, dbh, idesc, 1u);
                         }
-                        umma_commit(&empty_bar[s]);
-                        if (kc == kc_count - 1) umma_commit(&acc_full[ab]);
+                        umma_commit(&B->empty[s]);
+                        if (kc == kc_count - 1) umma_commit(&B->acc_full[ab]);
                     }
                     __syncwarp();
                 }
@@ -279,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(TcParams P)
     } else {
         // =============================== epilogue ===============================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int r = q * 32 + lane;            // row inside the tile
+        const int r = q * 32 + lane;
         float *my_tile = stat_tile + (warp - 5) * 32 * 33;
         uint32_t acc_it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
@@ -287,8 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(TcParams P)
             const bool row_ok = row < P.rows;
             for (int nt = 0; nt < P.n_tiles; nt++, acc_it++) {
                 const int ab = acc_it & 1;
-                const uint32_t aph = (acc_it >> 1) & 1;
-                mbar_wait(&acc_full[ab], aph);
+                mbar_wait(&B->acc_full[ab], (acc_it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT_MAX);
                 const int ncols = min(NT, P.N - nt * NT);
@@ -296,15 +349,40 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(TcParams P)
                     float v[32];
                     tmem_ld32(taddr + c0, v);
                     const int n0 = nt * NT + c0;
+                    float x1[32], x2[32];   // xhat terms for the dgrad statistics (dead code for kind 0)
+                    if (E.kind == RSB_EPI_BIAS_STATS) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int n = n0 + j;
-                        float y = v[j] + ((P.bias && n < P.N) ? __ldg(P.bias + n) : 0.f);
-                        v[j] = (row_ok && n < P.N) ? y : 0.f;
+                        for (int j = 0; j < 32; j++) {
+                            const int n = n0 + j;
+                            const float y = v[j] + ((E.bias && n < P.N) ? __ldg(E.bias + n) : 0.f);
+                            v[j] = (row_ok && n < P.N) ? y : 0.f;
+                        }
+                    } else {
+                        // dgrad: ReLU mask of the layer below from its stored pre-BN output, and xhat for BN backward
+                        const float *yl = E.Yl + (size_t)(row_ok ? row : 0) * E.ldl;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int n = n0 + j;
+                            float out = 0.f, h1 = 0.f, h2 = 0.f;
+                            if (row_ok && n < P.N) {
+                                const float y1 = __ldg(yl + n);
+                                float z = fmaf(y1, __ldg(E.sc + n), __ldg(E.sh + n));
+                                h1 = (y1 - __ldg(E.mu + n)) * __ldg(E.inv + n);
+                                if (E.dual) {
+                                    const float y2 = __ldg(yl + P.N + n);
+                                    z += fmaf(y2, __ldg(E.sc + P.N + n), __ldg(E.sh + P.N + n));
+                                    h2 = (y2 - __ldg(E.mu + P.N + n)) * __ldg(E.inv + P.N + n);
+                                }
+                                out = z > 0.f ? v[j] : 0.f;
+                            }
+                            v[j] = out;
+                            x1[j] = out * h1;
+                            x2[j] = out * h2;
+                        }
                     }
-                    if (row_ok) {
-                        float *yrow = P.Y + (size_t)row * P.N + n0;
-                        if (n0 + 32 <= P.N && (P.N & 3) == 0) {
+                    if (row_ok && E.Y) {
+                        float *yrow = E.Y + (size_t)row * E.ldy + n0;
+                        if (n0 + 32 <= P.N && ((uintptr_t)yrow & 15) == 0) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
                                 *reinterpret_cast<float4 *>(yrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -312,41 +390,162 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(TcParams P)
                             for (int j = 0; j < 32 && n0 + j < P.N; j++) yrow[j] = v[j];
                         }
                     }
-                    if (P.stats) {
-                        // column sums over this warp's 32 rows through a padded shared tile, then fp64 atomics
-#pragma unroll
-                        for (int j = 0; j < 32; j++) my_tile[lane * 33 + j] = v[j];
-                        __syncwarp();
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            const float t = my_tile[i * 33 + lane];
-                            s1 += t;
-                            s2 = fmaf(t, t, s2);
-                        }
-                        __syncwarp();
+                    if (E.stats) {
                         const int n = n0 + lane;
-                        if (n < P.N) {
-                            atomicAdd(P.stats + n, (double)s1);
-                            atomicAdd(P.stats + P.N + n, (double)s2);
+                        if (E.kind == RSB_EPI_BIAS_STATS) {
+                            float sq[32];
+#pragma unroll
+                            for (int j = 0; j < 32; j++) sq[j] = v[j] * v[j];
+                            const float s1 = warp_colsum(my_tile, v, lane), s2 = warp_colsum(my_tile, sq, lane);
+                            if (n < P.N) {
+                                atomicAdd(E.stats + n, (double)s1);
+                                atomicAdd(E.stats + P.N + n, (double)s2);
+                            }
+                        } else {
+                            const float s0 = warp_colsum(my_tile, v, lane), s1 = warp_colsum(my_tile, x1, lane);
+                            if (n < P.N) {
+                                atomicAdd(E.stats + n, (double)s0);
+                                atomicAdd(E.stats + P.N + n, (double)s1);
+                            }
+                            if (E.dual) {
+                                const float s2 = warp_colsum(my_tile, x2, lane);
+                                if (n < P.N) atomicAdd(E.stats + 2 * P.N + n, (double)s2);
+                            }
                         }
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[ab]);
+                mbar_arrive(&B->acc_empty[ab]);
             }
         }
     }
+    cta_epilogue(tmem_base, warp);
+}
 
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+// ============================================================================================================
+// dW[m, n] += sum_r G(r, m) * X(r, n)   (weight gradient; reduction over rows)
+// ============================================================================================================
+// Stage the TRANSPOSE of a [32 rows x width channels] slab as a K-major tile (channels = tile rows, the 32
+// reduction rows = K): lanes run along channels (coalesced global reads of one slab row), each thread packs 4
+// consecutive reduction rows of its channel into one 16 B core-matrix row.  Same canonical layout and
+// descriptors as gemm_rows (LBO 128 B, SBO 1024 B).
+__device__ __forceinline__ void wgrad_stage_operand(const Opnd &O, int width, int c_base, long row0, long rows,
+                                                    float *hi_base, float *lo_base, int warp, int lane)
+{
+    for (int k4 = warp; k4 < KC / 4; k4 += 4) {
+        const long r0 = row0 + k4 * 4;
+        for (int cb = 0; cb < width; cb += 32) {
+            const int ct = cb + lane;            // channel inside the tile
+            if (ct >= width) break;              // tiles are multiples of 16 channels, not of 32
+            const int c = c_base + ct;           // logical channel of the operand
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = (r0 + e < rows && c < O.K) ? opnd_load(O, r0 + e, O.k0 + c) : 0.f;
+            float4 hi, lo;
+            split4(v, hi, lo);
+            const int off = (ct >> 3) * (KC / 4) * 32 + k4 * 32 + (ct & 7) * 4;   // floats
+            *reinterpret_cast<float4 *>(hi_base + off) = hi;
+            *reinterpret_cast<float4 *>(lo_base + off) = lo;
+        }
     }
 }
 
-// W [N, K] (row-major, optionally transposed source) -> pre-split canonical chunks
+__global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_constant__ WgradParams P)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NT = P.NT;
+    const size_t a_bytes = A_TILE_BYTES;                  // one of hi / lo of the G^T tile (128 channels x 32 rows)
+    const size_t b_bytes = (size_t)NT * KC * 4;           // one of hi / lo of the X^T tile (NT channels x 32 rows)
+    const size_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    Barriers *B = reinterpret_cast<Barriers *>(smem + STAGES * stage_bytes);
+    const uint32_t tmem_base = cta_prologue(B, tid, warp);
+
+    const long n_chunks = (P.rows + KC - 1) / KC;
+    // chunks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (my_chunks > 0) {
+        if (warp < 4) {
+            uint32_t it = 0;
+            for (int mt = 0; mt < P.m_tiles; mt++)
+                for (int nt = 0; nt < P.n_tiles; nt++)
+                    for (long ci = 0; ci < my_chunks; ci++, it++) {
+                        const int s = it % STAGES;
+                        mbar_wait(&B->empty[s], ((it / STAGES) & 1) ^ 1);
+                        unsigned char *st = smem + (size_t)s * stage_bytes;
+                        const long row0 = (blockIdx.x + ci * gridDim.x) * (long)KC;
+                        wgrad_stage_operand(P.G, TM, mt * TM, row0, P.rows, reinterpret_cast<float *>(st),
+                                            reinterpret_cast<float *>(st + a_bytes), warp, lane);
+                        wgrad_stage_operand(P.X, NT, nt * NT, row0, P.rows, reinterpret_cast<float *>(st + 2 * a_bytes),
+                                            reinterpret_cast<float *>(st + 2 * a_bytes + b_bytes), warp, lane);
+                        fence_proxy_async();
+                        mbar_arrive(&B->full[s]);
+                        if (tid == 0) mbar_arrive(&B->full[s]);   // barrier counts 129 (shared with gemm_rows)
+                    }
+        } else if (warp == 4) {
+            const uint32_t idesc = umma_idesc_tf32(TM, NT, false);
+            uint32_t it = 0, acc_it = 0;
+            for (int mt = 0; mt < P.m_tiles; mt++)
+                for (int nt = 0; nt < P.n_tiles; nt++, acc_it++) {
+                    const int ab = acc_it & 1;
+                    mbar_wait(&B->acc_empty[ab], ((acc_it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(ab * NT_MAX);
+                    for (long ci = 0; ci < my_chunks; ci++, it++) {
+                        const int s = it % STAGES;
+                        mbar_wait(&B->full[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t st = rsb_smem_addr(smem + (size_t)s * stage_bytes);
+                            const uint32_t a_hi = st, a_lo = st + (uint32_t)a_bytes;
+                            const uint32_t b_hi = st + 2 * (uint32_t)a_bytes, b_lo = b_hi + (uint32_t)b_bytes;
+#pragma unroll
+                            for (int ks = 0; ks < KC / 8; ks++) {
+                                const uint32_t koff = ks * 2 * 128, SBO = (KC / 4) * 128, LBO = 128;
+                                const uint64_t dah = umma_desc(a_hi + koff, LBO, SBO), dal = umma_desc(a_lo + koff, LBO, SBO);
+                                const uint64_t dbh = umma_desc(b_hi + koff, LBO, SBO), dbl = umma_desc(b_lo + koff, LBO, SBO);
+                                umma_tf32(tmem_d, dal, dbh, idesc, (ci | ks) ? 1u : 0u);
+                                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                            }
+                            umma_commit(&B->empty[s]);
+                            if (ci == my_chunks - 1) umma_commit(&B->acc_full[ab]);
+                        }
+                        __syncwarp();
+                    }
+                }
+        } else {
+            const int q = warp & 3;
+            const int r = q * 32 + lane;            // output channel inside the M tile
+            uint32_t acc_it = 0;
+            for (int mt = 0; mt < P.m_tiles; mt++)
+                for (int nt = 0; nt < P.n_tiles; nt++, acc_it++) {
+                    const int ab = acc_it & 1;
+                    mbar_wait(&B->acc_full[ab], (acc_it >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT_MAX);
+                    const int m = mt * TM + r;
+                    const int ncols = min(NT, P.N - nt * NT);
+                    for (int c0 = 0; c0 < ncols; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + c0, v);
+                        if (m < P.M) {
+                            float *dst = P.dW + (size_t)m * P.ldw + nt * NT + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (c0 + j < ncols) atomicAdd(dst + j, v[j]);
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&B->acc_empty[ab]);
+                }
+        }
+    }
+    cta_epilogue(tmem_base, warp);
+}
+
+// W [N, K] (row-major, optionally transposed source) -> pre-split canonical K-major chunks
 __global__ void weight_prep_kernel(const float *__restrict__ W, int N, int K, int ldw, int transposed, int NT,
                                    int n_tiles, int k_chunks, float *__restrict__ Wp)
 {
@@ -359,14 +558,7 @@ __global__ void weight_prep_kernel(const float *__restrict__ W, int N, int K, in
         const int n = nt * NT + nn, k = kc * KC + kk;
         float w = 0.f;
         if (n < N && k < K) w = transposed ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k];
-        float hi, lo;
-        {
-            uint32_t r;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w));
-            hi = __uint_as_float(r);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w - hi));
-            lo = __uint_as_float(r);
-        }
+        const float hi = to_tf32(w), lo = to_tf32(w - hi);
         // canonical K-major no-swizzle: core matrix (nn/8, kk/4) at (nn/8)*SBO + (kk/4)*128 B, row (nn%8)*16 B
         const size_t off = (size_t)(nn >> 3) * ((KC / 4) * 32) + (size_t)(kk >> 2) * 32 + (nn & 7) * 4 + (kk & 3);
         float *blk = Wp + ((size_t)nt * k_chunks + kc) * (2 * (size_t)NT * KC);
@@ -376,26 +568,32 @@ __global__ void weight_prep_kernel(const float *__restrict__ W, int N, int K, in
 }
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int pick_nt(int N) { return N <= NT_MAX ? round_up(N, 16) : NT_MAX; }
+
+int check_opnd(const Opnd &O, const char *what)
+{
+    if (O.K < 1 || O.kind < 0 || O.kind > RSB_OPND_POOLED) { rsb_set_error("%s: bad operand descriptor", what); return 1; }
+    if (!O.U) { rsb_set_error("%s: operand U is null", what); return 1; }
+    if (O.kind != RSB_OPND_RAW && (!O.a || !O.d)) { rsb_set_error("%s: operand needs coefficient vectors", what); return 1; }
+    if ((O.kind == RSB_OPND_AFFINE2 || O.kind == RSB_OPND_POOLED) && (!O.V || !O.b || O.ku < 1)) { rsb_set_error("%s: affine operand needs V, b, ku", what); return 1; }
+    if (O.kind == RSB_OPND_POOLED && (!O.arg || O.ns < 1)) { rsb_set_error("%s: pooled operand needs arg, ns", what); return 1; }
+    return 0;
+}
 
 }  // namespace
 
-// Size (in floats) of the pre-split weight buffer for an [N, K] weight.
 RSB_EXPORT long rsb_linear_tc_weight_floats(int N, int K)
 {
-    const int NT = N <= NT_MAX ? round_up(N, 16) : NT_MAX;
-    const int n_tiles = (N + NT - 1) / NT;
-    const int k_chunks = (K + KC - 1) / KC;
-    return (long)n_tiles * k_chunks * 2 * NT * KC;
+    const int NT = pick_nt(N);
+    return (long)((N + NT - 1) / NT) * ((K + KC - 1) / KC) * 2 * NT * KC;
 }
 
-// W: [N, K] row-major with leading dimension ldw (transposed != 0: W is stored [K, N] and used as its transpose).
 RSB_EXPORT int rsb_linear_tc_prep_weight(int N, int K, const float *W, int ldw, int transposed, float *Wp,
                                          cudaStream_t stream)
 {
     RSB_REQUIRE(N >= 1 && K >= 1, "bad sizes");
-    const int NT = N <= NT_MAX ? round_up(N, 16) : NT_MAX;
-    const int n_tiles = (N + NT - 1) / NT;
-    const int k_chunks = (K + KC - 1) / KC;
+    const int NT = pick_nt(N);
+    const int n_tiles = (N + NT - 1) / NT, k_chunks = (K + KC - 1) / KC;
     const long total = (long)n_tiles * k_chunks * NT * KC;
     const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     weight_prep_kernel<<<grid, 256, 0, stream>>>(W, N, K, ldw, transposed, NT, n_tiles, k_chunks, Wp);
@@ -404,32 +602,68 @@ RSB_EXPORT int rsb_linear_tc_prep_weight(int N, int K, const float *W, int ldw, 
     return 0;
 }
 
-// Y[rows,N] = act(X)[rows,K] @ W[N,K]^T + bias; stats (fp64 [2N], caller-zeroed) += column sum / sum of squares.
-// mode 0: act = identity; 1: relu(x*sc+sh), sc/sh [K]; 2: relu(x[:, :K]*sc[:K]+sh[:K] + x[:, K:2K]*sc[K:]+sh[K:]).
-RSB_EXPORT int rsb_linear_tc_forward(long rows, int K, int N, const float *X, int ldx, const float *Wp,
-                                     const float *bias, int mode, const float *sc, const float *sh, float *Y,
-                                     double *stats, cudaStream_t stream)
+RSB_EXPORT int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float *Wp, const rsb_epi_t *E,
+                             cudaStream_t stream)
 {
-    RSB_REQUIRE(rows >= 0 && K >= 1 && N >= 1, "bad sizes");
-    RSB_REQUIRE(mode >= 0 && mode <= 2, "bad mode");
-    RSB_REQUIRE(mode == 0 || (sc && sh), "prologue needs scale/shift");
+    RSB_REQUIRE(rows >= 0 && N >= 1 && A && E && Wp, "bad arguments");
+    if (check_opnd(*A, "rsb_gemm_rows")) return (int)cudaErrorInvalidValue;
+    RSB_REQUIRE(E->kind == RSB_EPI_BIAS_STATS || (E->Yl && E->sc && E->sh && E->mu && E->inv), "dgrad epilogue needs Yl/sc/sh/mu/inv");
     if (rows == 0) return 0;
-    TcParams P = {};
-    P.X = X; P.Wp = Wp; P.bias = bias; P.sc = sc; P.sh = sh; P.Y = Y; P.stats = stats;
-    P.rows = rows; P.K = K; P.ldx = ldx; P.N = N; P.mode = mode;
-    P.NT = N <= NT_MAX ? round_up(N, 16) : NT_MAX;
+    RowsParams P;
+    P.A = *A; P.E = *E; P.Wp = Wp; P.rows = rows; P.N = N;
+    P.NT = pick_nt(N);
     P.n_tiles = (N + P.NT - 1) / P.NT;
-    P.k_chunks = (K + KC - 1) / KC;
-    const size_t smem = STAGES * (2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4) + 256 + 4 * 32 * 33 * 4;
+    P.k_chunks = (A->K + KC - 1) / KC;
+    const size_t smem = STAGES * (2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4) + sizeof(Barriers) + 4 * 32 * 33 * 4;
     static bool attr_set = false;
     if (!attr_set) {
-        RSB_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RSB_CUDA(cudaFuncSetAttribute(gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const long n_row_tiles = (rows + TM - 1) / TM;
     const int grid = (int)(n_row_tiles < rsb_sm_count() ? n_row_tiles : rsb_sm_count());
-    linear_tc_kernel<<<grid, THREADS, smem, stream>>>(P);
-    RSB_CHECK_LAUNCH("linear_tc_kernel");
+    gemm_rows_kernel<<<grid, THREADS, smem, stream>>>(P);
+    RSB_CHECK_LAUNCH("gemm_rows_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;
+}
+
+RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, float *dW, int ldw,
+                              cudaStream_t stream)
+{
+    RSB_REQUIRE(rows >= 0 && G && X && dW, "bad arguments");
+    if (check_opnd(*G, "rsb_gemm_wgrad(G)") || check_opnd(*X, "rsb_gemm_wgrad(X)")) return (int)cudaErrorInvalidValue;
+    if (rows == 0) return 0;
+    WgradParams P;
+    P.G = *G; P.X = *X; P.dW = dW; P.ldw = ldw; P.rows = rows;
+    P.M = G->K; P.N = X->K;
+    P.NT = pick_nt(P.N);
+    P.m_tiles = (P.M + TM - 1) / TM;
+    P.n_tiles = (P.N + P.NT - 1) / P.NT;
+    const size_t smem = STAGES * (2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4) + sizeof(Barriers);
+    static bool attr_set = false;
+    if (!attr_set) {
+        RSB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const long n_chunks = (rows + KC - 1) / KC;
+    const int grid = (int)(n_chunks < rsb_sm_count() ? n_chunks : rsb_sm_count());
+    gemm_wgrad_kernel<<<grid, THREADS, smem, stream>>>(P);
+    RSB_CHECK_LAUNCH("gemm_wgrad_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+// convenience entry kept from the first bring-up: Y = act(X) @ W^T + bias with modes 0/1/2 (see header)
+RSB_EXPORT int rsb_linear_tc_forward(long rows, int K, int N, const float *X, int ldx, const float *Wp,
+                                     const float *bias, int mode, const float *sc, const float *sh, float *Y,
+                                     double *stats, cudaStream_t stream)
+{
+    RSB_REQUIRE(mode >= 0 && mode <= 2, "bad mode");
+    rsb_opnd_t A = {};
+    A.U = X; A.ldu = ldx; A.K = K; A.ku = K; A.a = sc; A.d = sh;
+    A.kind = mode == 0 ? RSB_OPND_RAW : (mode == 1 ? RSB_OPND_BN_RELU : RSB_OPND_DUAL_BN_RELU);
+    rsb_epi_t E = {};
+    E.Y = Y; E.ldy = N; E.bias = bias; E.stats = stats; E.kind = RSB_EPI_BIAS_STATS;
+    return rsb_gemm_rows(rows, N, &A, Wp, &E, stream);
 }

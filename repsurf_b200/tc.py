@@ -1,20 +1,74 @@
-"""Python face of the tcgen05 shared-MLP kernels (csrc/mlp_tc.cu) — thin, allocation + launch only."""
+"""Python face of the tcgen05 shared-MLP kernels (csrc/mlp_tc.cu, csrc/mlp_aux.cu): descriptor structs,
+launch helpers, and the fused shared-MLP autograd function used by the SurfaceAbstractionCD modules.
+
+Nothing here computes on the host or through torch GEMM/BatchNorm kernels: torch only allocates."""
+import ctypes
+
 import torch
+from torch.autograd import Function
 
 from . import _native as N
 
+OPND_RAW, OPND_BN_RELU, OPND_DUAL, OPND_AFFINE2, OPND_POOLED = 0, 1, 2, 3, 4
+EPI_BIAS_STATS, EPI_RELU_MASK = 0, 1
+
+
+class Opnd(ctypes.Structure):
+    _fields_ = [("U", ctypes.c_void_p), ("V", ctypes.c_void_p), ("a", ctypes.c_void_p), ("b", ctypes.c_void_p),
+                ("d", ctypes.c_void_p), ("arg", ctypes.c_void_p), ("ldu", ctypes.c_int), ("ldv", ctypes.c_int),
+                ("K", ctypes.c_int), ("k0", ctypes.c_int), ("ku", ctypes.c_int), ("kind", ctypes.c_int),
+                ("ns", ctypes.c_int)]
+
+
+class Epi(ctypes.Structure):
+    _fields_ = [("Y", ctypes.c_void_p), ("ldy", ctypes.c_int), ("bias", ctypes.c_void_p), ("stats", ctypes.c_void_p),
+                ("Yl", ctypes.c_void_p), ("ldl", ctypes.c_int), ("sc", ctypes.c_void_p), ("sh", ctypes.c_void_p),
+                ("mu", ctypes.c_void_p), ("inv", ctypes.c_void_p), ("kind", ctypes.c_int), ("dual", ctypes.c_int)]
+
+
+def _dp(t, off=0):
+    return None if t is None else t.data_ptr() + 4 * off
+
+
+def opnd(kind, U, K, a=None, d=None, V=None, b=None, arg=None, ku=None, k0=0, ns=1):
+    o = Opnd()
+    o.U, o.V, o.a, o.b, o.d, o.arg = _dp(U), _dp(V), _dp(a), _dp(b), _dp(d), (None if arg is None else arg.data_ptr())
+    o.ldu = U.stride(0)
+    o.ldv = 0 if V is None else V.stride(0)
+    o.K, o.k0, o.ku, o.kind, o.ns = K, k0, (K if ku is None else ku), kind, ns
+    o._keep = (U, V, a, b, d, arg)
+    return o
+
 
 def prep_weight(W, transposed=False):
-    """W [N,K] (or [K,N] when transposed) fp32 -> pre-split hi/lo tf32 operand buffer for linear_forward."""
-    W = W.detach()
+    """W [N,K] (or stored [K,N] when transposed) fp32 -> pre-split hi/lo tf32 operand buffer."""
+    W = W.detach().contiguous()
     if transposed:
         K, Nn = W.shape
     else:
         Nn, K = W.shape
-    W = W.contiguous()
     buf = torch.empty(int(N.lib().rsb_linear_tc_weight_floats(Nn, K)), dtype=torch.float32, device=W.device)
     N.call("rsb_linear_tc_prep_weight", Nn, K, W, W.shape[1], 1 if transposed else 0, buf)
     return buf, Nn, K
+
+
+def gemm_rows(rows, Nn, A, Wp, Y=None, ldy=None, y_off=0, bias=None, stats=None, mask=None):
+    """Y[:, y_off:y_off+N] = A @ W^T (+bias) ; mask = (Yl, sc, sh, mu, inv, dual) selects the dgrad epilogue."""
+    e = Epi()
+    e.Y = _dp(Y, y_off)
+    e.ldy = (Y.stride(0) if ldy is None else ldy) if Y is not None else 0
+    e.bias, e.stats = _dp(bias), (None if stats is None else stats.data_ptr())
+    if mask is None:
+        e.kind, e.dual = EPI_BIAS_STATS, 0
+    else:
+        Yl, sc, sh, mu, inv, dual = mask
+        e.Yl, e.ldl, e.sc, e.sh, e.mu, e.inv = _dp(Yl), Yl.stride(0), _dp(sc), _dp(sh), _dp(mu), _dp(inv)
+        e.kind, e.dual = EPI_RELU_MASK, int(dual)
+    N.call("rsb_gemm_rows", rows, Nn, A, Wp, e)
+
+
+def gemm_wgrad(rows, G, X, dW):
+    N.call("rsb_gemm_wgrad", rows, G, X, dW, dW.stride(0))
 
 
 def linear_forward(X, W, bias=None, mode=0, sc=None, sh=None, want_stats=False, prepped=None):
@@ -26,3 +80,182 @@ def linear_forward(X, W, bias=None, mode=0, sc=None, sh=None, want_stats=False, 
     stats = torch.zeros(2 * Nn, dtype=torch.float64, device=X.device) if want_stats else None
     N.call("rsb_linear_tc_forward", rows, K, Nn, X, X.shape[1], Wp, bias, mode, sc, sh, Y, stats)
     return Y, stats
+
+
+def _bn_finalize(C, rows, stats, gamma, beta, eps, momentum, rm, rv, dev):
+    out = torch.empty(4, C, dtype=torch.float32, device=dev)
+    N.call("rsb_bn_finalize", C, rows, stats, gamma, beta, float(eps), float(momentum), rm, rv, out[0], out[1], out[2], out[3])
+    return out[0], out[1], out[2], out[3]
+
+
+def _bn_eval_coef(bn_list):
+    """eval mode: scale/shift from the running statistics (tiny per-channel math)."""
+    g = torch.cat([b.weight for b in bn_list]).detach()
+    be = torch.cat([b.bias for b in bn_list]).detach()
+    rm = torch.cat([b.running_mean for b in bn_list])
+    rv = torch.cat([b.running_var for b in bn_list])
+    inv = torch.rsqrt(rv + bn_list[0].eps)
+    sc = g * inv
+    return sc.contiguous(), (be - rm * sc).contiguous(), rm.contiguous(), inv.contiguous()
+
+
+class _FusedSAMLP(Function):
+    """relu(bn_l(X_pos W_l^T) + bn_f(X_feat W_f^T)) -> [relu(bn(. W_i^T))]* -> max over nsample, fused.
+
+    forward(X [R, Cin], meta, *params) with params = W_l, b_l, W_f, b_f, g_l, be_l, g_f, be_f, then (W, b, g, be) per
+    further layer.  Running statistics are updated by the caller from the returned batch statistics."""
+
+    @staticmethod
+    def forward(ctx, X, meta, *params):
+        ns, P, eps, n_extra = meta["ns"], meta["pos_channel"], meta["eps"], meta["n_extra"]
+        dev = X.device
+        R, Cin = X.shape
+        G = R // ns
+        W_l, b_l, W_f, b_f, g_l, be_l, g_f, be_f = params[:8]
+        C0 = W_l.shape[0]
+        W_l2, W_f2 = W_l.reshape(C0, -1), W_f.reshape(C0, -1)
+        F = Cin - P
+        # block-diagonal first layer: one GEMM produces [y_l | y_f]
+        Wbd = torch.zeros(2 * C0, Cin, device=dev)
+        Wbd[:C0, :P] = W_l2
+        Wbd[C0:, P:] = W_f2
+        bias0 = torch.cat([b_l, b_f]).detach()
+        Wp0, _, _ = prep_weight(Wbd)
+        Y0 = torch.empty(R, 2 * C0, device=dev)
+        st = torch.zeros(4 * C0, dtype=torch.float64, device=dev)
+        gemm_rows(R, 2 * C0, opnd(OPND_RAW, X, Cin), Wp0, Y=Y0, bias=bias0, stats=st)
+        coefs = [_bn_finalize(2 * C0, R, st, torch.cat([g_l, g_f]).detach(), torch.cat([be_l, be_f]).detach(), eps, 0.0,
+                              None, None, dev)]
+        batch_stats = [st]
+        Ys = [Y0]
+        Ws = []
+        prev = opnd(OPND_DUAL, Y0, C0, a=coefs[0][0], d=coefs[0][1], ku=C0)
+        Cprev = C0
+        for i in range(n_extra):
+            W, b, g, be = params[8 + 4 * i: 12 + 4 * i]
+            Ci = W.shape[0]
+            W2 = W.reshape(Ci, -1).detach().contiguous()
+            Wp, _, _ = prep_weight(W2)
+            Yi = torch.empty(R, Ci, device=dev)
+            sti = torch.zeros(2 * Ci, dtype=torch.float64, device=dev)
+            gemm_rows(R, Ci, prev, Wp, Y=Yi, bias=b.detach(), stats=sti)
+            co = _bn_finalize(Ci, R, sti, g.detach(), be.detach(), eps, 0.0, None, None, dev)
+            coefs.append(co)
+            batch_stats.append(sti)
+            Ys.append(Yi)
+            Ws.append(W2)
+            prev = opnd(OPND_BN_RELU, Yi, Ci, a=co[0], d=co[1])
+            Cprev = Ci
+        out = torch.empty(G, Cprev, device=dev)
+        arg = torch.empty(G, Cprev, dtype=torch.int32, device=dev)
+        N.call("rsb_pool_forward", G, ns, Cprev, Ys[-1], Ys[-1].stride(0), coefs[-1][0], coefs[-1][1], out, arg)
+        ctx.meta = meta
+        ctx.saved = (X, Wbd, Ws, Ys, coefs, arg)
+        ctx.mark_non_differentiable(*batch_stats)
+        return (out, *batch_stats)
+
+    @staticmethod
+    def backward(ctx, dOut, *_unused):
+        meta = ctx.meta
+        ns, P, n_extra = meta["ns"], meta["pos_channel"], meta["n_extra"]
+        X, Wbd, Ws, Ys, coefs, arg = ctx.saved
+        dev = X.device
+        R, Cin = X.shape
+        G = R // ns
+        C0 = Wbd.shape[0] // 2
+        L = n_extra  # index of the last layer (0 = block-diagonal first layer)
+        CL = Ys[L].shape[1]
+        sc, sh, mu, inv = coefs[L]
+        grads = {}
+        # ---- max-pool backward -> BatchNorm-backward coefficients of the last layer
+        st = torch.zeros(2 * CL, dtype=torch.float64, device=dev)
+        dm = torch.empty(G, CL, device=dev)
+        N.call("rsb_pool_backward_stats", G, ns, CL, dOut.contiguous(), arg, Ys[L], Ys[L].stride(0), sc, sh, mu, inv, dm, st)
+        co = torch.empty(5, CL, device=dev)
+        N.call("rsb_bn_backward_coef", CL, R, st, 0, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
+        grads[("g", L)], grads[("be", L)] = co[3], co[4]
+        Gop = opnd(OPND_POOLED, dm, CL, a=co[0], b=co[1], d=co[2], V=Ys[L], arg=arg, ns=ns) if L > 0 else None
+        if L == 0:
+            raise RuntimeError("shared MLP needs at least two layers")
+        for l in range(L, 0, -1):
+            W = Ws[l - 1]                                   # [C_l, C_{l-1}]
+            Cl, Cp = W.shape
+            # forward operand of layer l (= activated output of layer l-1)
+            if l - 1 == 0:
+                Aprev = opnd(OPND_DUAL, Ys[0], C0, a=coefs[0][0], d=coefs[0][1], ku=C0)
+            else:
+                Aprev = opnd(OPND_BN_RELU, Ys[l - 1], Cp, a=coefs[l - 1][0], d=coefs[l - 1][1])
+            dW = torch.zeros(Cl, Cp, device=dev)
+            gemm_wgrad(R, Gop, Aprev, dW)
+            grads[("W", l)] = dW
+            # dgrad through W_l, ReLU mask + BatchNorm-backward statistics of layer l-1
+            WpT, _, _ = prep_weight(W, transposed=True)      # operand [N=C_{l-1}, K=C_l]
+            dual = (l - 1 == 0)
+            dZ = torch.empty(R, Cp, device=dev)
+            stp = torch.zeros((3 if dual else 2) * Cp, dtype=torch.float64, device=dev)
+            scp, shp, mup, invp = coefs[l - 1]
+            gemm_rows(R, Cp, Gop, WpT, Y=dZ, stats=stp, mask=(Ys[l - 1], scp, shp, mup, invp, dual))
+            width = 2 * Cp if dual else Cp
+            cop = torch.empty(5, width, device=dev)
+            N.call("rsb_bn_backward_coef", Cp, R, stp, 1 if dual else 0, scp, mup, invp, cop[0], cop[1], cop[2], cop[3], cop[4])
+            grads[("g", l - 1)], grads[("be", l - 1)] = cop[3], cop[4]
+            Gop = opnd(OPND_AFFINE2, dZ, width, a=cop[0], b=cop[1], d=cop[2], V=Ys[l - 1], ku=Cp)
+            dZ0, cop0 = dZ, cop
+        # ---- first layer: weight gradient of the block-diagonal GEMM, input gradient of the feature columns
+        dWbd = torch.zeros(2 * C0, Cin, device=dev)
+        gemm_wgrad(R, Gop, opnd(OPND_RAW, X, Cin), dWbd)
+        dX = None
+        if ctx.needs_input_grad[0]:
+            F = Cin - P
+            dX = torch.zeros(R, Cin, device=dev)
+            Wf = Wbd[C0:, P:].contiguous()                   # [C0, F]
+            WpT, _, _ = prep_weight(Wf, transposed=True)     # operand [N=F, K=C0]
+            Gf = opnd(OPND_AFFINE2, dZ0, C0, a=cop0[0], b=cop0[1], d=cop0[2], V=Ys[0], ku=C0, k0=C0)
+            gemm_rows(R, F, Gf, WpT, Y=dX, ldy=Cin, y_off=P)
+        # ---- assemble parameter gradients in the order of *params
+        W_l_shape, W_f_shape = meta["W_l_shape"], meta["W_f_shape"]
+        zero = lambda n: torch.zeros(n, device=dev)
+        out = [dX, None,
+               dWbd[:C0, :P].reshape(W_l_shape), zero(C0), dWbd[C0:, P:].reshape(W_f_shape), zero(C0),
+               grads[("g", 0)][:C0], grads[("be", 0)][:C0], grads[("g", 0)][C0:], grads[("be", 0)][C0:]]
+        for i in range(n_extra):
+            out += [grads[("W", i + 1)].reshape(meta["W_shapes"][i]), zero(grads[("W", i + 1)].shape[0]),
+                    grads[("g", i + 1)], grads[("be", i + 1)]]
+        return tuple(out)
+
+
+def _update_running(bn, mean, var_unbiased):
+    if bn.track_running_stats and bn.running_mean is not None:
+        m = bn.momentum if bn.momentum is not None else 0.1
+        bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+        bn.running_var.mul_(1 - m).add_(var_unbiased, alpha=m)
+        bn.num_batches_tracked.add_(1)
+
+
+def sa_mlp_fused(rows, pos_channel, mod, nsample):
+    """Drop-in for mlp.sa_mlp_rows on the tensor cores (training mode).  rows [G*nsample, C] -> [G, mlp[-1]]."""
+    bns = [mod.bn_l0, mod.bn_f0] + list(mod.mlp_bns)
+    params = [mod.mlp_l0.weight, mod.mlp_l0.bias, mod.mlp_f0.weight, mod.mlp_f0.bias,
+              mod.bn_l0.weight, mod.bn_l0.bias, mod.bn_f0.weight, mod.bn_f0.bias]
+    for lin, bn in zip(mod.mlp_convs, mod.mlp_bns):
+        params += [lin.weight, lin.bias, bn.weight, bn.bias]
+    meta = dict(ns=nsample, pos_channel=pos_channel, eps=mod.bn_l0.eps, n_extra=len(mod.mlp_convs),
+                W_l_shape=tuple(mod.mlp_l0.weight.shape), W_f_shape=tuple(mod.mlp_f0.weight.shape),
+                W_shapes=[tuple(l.weight.shape) for l in mod.mlp_convs])
+    res = _FusedSAMLP.apply(rows.contiguous(), meta, *params)
+    out, stats = res[0], res[1:]
+    # running statistics (same side effects as the BatchNorm modules): batch mean, UNBIASED batch variance
+    R = rows.shape[0]
+    with torch.no_grad():
+        C0 = mod.mlp_l0.weight.shape[0]
+        st0 = stats[0]
+        mean0 = st0[:2 * C0] / R
+        var0 = (st0[2 * C0:] / R - mean0 * mean0).clamp_min(0) * (R / max(R - 1, 1))
+        _update_running(mod.bn_l0, mean0[:C0].float(), var0[:C0].float())
+        _update_running(mod.bn_f0, mean0[C0:].float(), var0[C0:].float())
+        for bn, sti in zip(mod.mlp_bns, stats[1:]):
+            C = sti.shape[0] // 2
+            mean = sti[:C] / R
+            var = (sti[C:] / R - mean * mean).clamp_min(0) * (R / max(R - 1, 1))
+            _update_running(bn, mean.float(), var.float())
+    return out

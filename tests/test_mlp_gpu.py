@@ -49,3 +49,56 @@ def test_linear_tc_prologue_modes(rows, K, N, mode):
 def test_linear_tc_many_tiles_persistent():
     # more row tiles than SMs: exercises the persistent loop, both accumulator buffers and stage phases
     _run(148 * 128 * 3 + 77, 40, 48, 1, seed=3)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused shared MLP (forward + backward on tcgen05) vs the same block in torch fp64
+# ------------------------------------------------------------------------------------------------------------
+class _Block(torch.nn.Module):
+    def __init__(self, pos_c, feat_c, mlp, conv):
+        super().__init__()
+        import torch.nn as nn
+        Conv, BN = (nn.Conv2d, nn.BatchNorm2d) if conv == 2 else (nn.Conv1d, nn.BatchNorm1d)
+        self.mlp_l0, self.mlp_f0 = Conv(pos_c, mlp[0], 1), Conv(feat_c, mlp[0], 1)
+        self.bn_l0, self.bn_f0 = BN(mlp[0]), BN(mlp[0])
+        self.mlp_convs = nn.ModuleList(Conv(i, o, 1) for i, o in zip(mlp[:-1], mlp[1:]))
+        self.mlp_bns = nn.ModuleList(BN(o) for o in mlp[1:])
+        for m in self.modules():
+            if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                torch.nn.init.uniform_(m.weight, 0.5, 1.5)
+                torch.nn.init.normal_(m.bias, 0, 0.2)
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("G,ns,pos_c,feat_c,mlp,conv", [(300, 32, 3, 16, [32, 32, 64], 1), (64, 64, 6, 138, [128, 128, 256], 2),
+                                                         (40, 32, 3, 266, [256, 256, 512], 1), (1000, 16, 6, 10, [64, 64, 128], 2)])
+def test_fused_sa_mlp_matches_fp64_torch(G, ns, pos_c, feat_c, mlp, conv):
+    import copy
+    from repsurf_b200 import tc
+    from repsurf_b200.mlp import sa_mlp_rows
+    torch.manual_seed(G + ns)
+    blk = _Block(pos_c, feat_c, mlp, conv).to(cuda).train()
+    ref = copy.deepcopy(blk).double()
+    X = torch.randn(G * ns, pos_c + feat_c, device=cuda)
+    Xa = X.clone().requires_grad_(True)
+    Xb = X.double().requires_grad_(True)
+    out = tc.sa_mlp_fused(Xa, pos_c, blk, ns)
+    want = sa_mlp_rows(Xb, pos_c, ref, ns)
+    assert _rel(out, want) < 1e-5
+    go = torch.randn_like(out)
+    out.backward(go)
+    want.backward(go.double())
+    # running statistics (side effects of train-mode BatchNorm)
+    for a, b in zip(blk.buffers(), ref.buffers()):
+        assert _rel(a.double(), b) < 1e-5 or a.dtype == torch.int64 and int(a) == int(b)
+    # gradients: feature columns of X (position columns carry none on the RepSurf path), weights, BN affine
+    assert _rel(Xa.grad[:, pos_c:], Xb.grad[:, pos_c:]) < 2e-4
+    assert float(Xa.grad[:, :pos_c].abs().max()) == 0.0
+    for (n, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        if n.endswith("bias") and "bn" not in n:
+            assert float(p.grad.abs().max()) == 0.0 and float(q.grad.abs().max()) < 1e-6 * max(1.0, float(go.abs().sum()))
+        else:
+            assert _rel(p.grad, q.grad) < 2e-4, n
