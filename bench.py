@@ -68,7 +68,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -94,11 +94,13 @@ class ClockSampler:
 class EntryTimer:
     """CUDA-event timing of every C-ABI call made through repsurf_b200._native.call (torch's current stream)."""
 
-    def __init__(self, native):
-        self.native, self.orig, self.ev = native, native.call, []
+    def __init__(self, native, only=None):
+        self.native, self.orig, self.ev, self.only = native, native.call, [], only
 
     def __enter__(self):
         def timed(name, *args):
+            if self.only is not None and name not in self.only:
+                return self.orig(name, *args)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             self.orig(name, *args)
@@ -286,10 +288,12 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("RSB_NO_CLOCKS"):
         clocks.start()
     _native.reset_launch_count()
-    with EntryTimer(_native) as et:
+    timed_entries = None if os.environ.get("RSB_TIME_ALL_ENTRIES") else {
+        "rsb_furthestsampling_packed", "rsb_furthestsampling_dense", "rsb_knnquery_packed", "rsb_knnquery_dense"}
+    with EntryTimer(_native, timed_entries) as et:
         ms_step = timed(step_resident, args.steps)
     launches = _native.launch_count()
     per_entry = et.summary()

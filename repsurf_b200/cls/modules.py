@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from . import pointops as P
 from ..seg import pointops as PP
 from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, linear_rows, sa_mlp_rows
+from ..mlp import bn_rows, linear_rows, sa_mlp
 
 
 def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_normal, return_polar):
@@ -96,7 +96,7 @@ class SurfaceAbstractionCD(nn.Module):
                                                            feature, self.return_normal, self.return_polar)
             groups, ns = self.npoint, self.nsample
         # channel de-differentiation: position and feature channels get their own first layer (:236-239)
-        pooled = sa_mlp_rows(rows, self.pos_channel, self, ns)                # [B*groups, C']
+        pooled = sa_mlp(rows, self.pos_channel, self, ns)                # [B*groups, C']
         return new_center, new_normal, pooled.view(B, groups, -1).transpose(1, 2).contiguous()
 
 

@@ -36,7 +36,10 @@ constexpr int KC = 32;           // reduction elements per pipeline chunk (4 UMM
 constexpr int STAGES = 2;
 constexpr int NT_MAX = 256;      // UMMA N <= 256
 constexpr int A_TILE_BYTES = TM * KC * 4;           // 16 KB (one of hi / lo), K-major tiles
-constexpr int THREADS = 9 * 32;
+constexpr int PROD_WARPS = 8;                      // operand-staging warps
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int MMA_WARP = PROD_WARPS;               // warp index of the MMA issuer
+constexpr int THREADS = (PROD_WARPS + 1 + 4) * 32; // + 4 epilogue warps
 
 typedef rsb_opnd_t Opnd;
 typedef rsb_epi_t Epi;
@@ -159,29 +162,117 @@ __device__ __forceinline__ float to_tf32(float x)
 }
 
 // ---- operand transform ------------------------------------------------------------------------------------
-// value of logical element (row r, channel k) of an operand; k already includes O.k0; caller guarantees r < rows.
-__device__ __forceinline__ float opnd_load(const Opnd &O, long r, int k)
+// Per-channel coefficients are hoisted into registers once per (thread, chunk); loads are 128-bit when the
+// operand's row pitch and channel offset allow it.
+struct Coef4 {
+    float a[4], b[4], d[4], a2[4], d2[4];
+};
+
+__device__ __forceinline__ void coef_load(const Opnd &O, int k, int nv, Coef4 &c)
+{
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const bool ok = e < nv;
+        c.a[e] = (ok && O.a) ? __ldg(O.a + k + e) : 0.f;
+        c.d[e] = (ok && O.d) ? __ldg(O.d + k + e) : 0.f;
+        c.b[e] = (ok && O.b) ? __ldg(O.b + k + e) : 0.f;
+        if (O.kind == RSB_OPND_DUAL_BN_RELU) {
+            c.a2[e] = ok ? __ldg(O.a + O.ku + k + e) : 0.f;
+            c.d2[e] = ok ? __ldg(O.d + O.ku + k + e) : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void ld4(const float *p, bool vec, int nv, float *v)
+{
+    if (vec) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = e < nv ? __ldg(p + e) : 0.f;
+    }
+}
+
+struct OpndFlags {
+    bool vecU, vecV, vecU2;
+};
+
+__device__ __forceinline__ OpndFlags opnd_flags(const Opnd &O)
+{
+    OpndFlags f;
+    const bool k0ok = (O.k0 & 3) == 0;
+    f.vecU = k0ok && (O.ldu & 3) == 0 && ((uintptr_t)O.U & 15) == 0 && (O.kind != RSB_OPND_AFFINE2 || (O.ku & 3) == 0);
+    f.vecU2 = f.vecU && (O.ku & 3) == 0;
+    f.vecV = k0ok && O.V && (O.ldv & 3) == 0 && ((uintptr_t)O.V & 15) == 0;
+    return f;
+}
+
+// 4 consecutive channels k..k+3 (k includes k0, k % 4 == 0 relative to k0) of row r; nv = valid channels.
+// (g, sidx) = pooling group of r and its sample index inside the group (POOLED only).
+__device__ __forceinline__ void opnd_eval4(const Opnd &O, const OpndFlags &F, const Coef4 &c, long r, int k, int nv,
+                                           long g, int sidx, float *v)
+{
+    float u[4];
+    switch (O.kind) {
+    case RSB_OPND_RAW:
+        ld4(O.U + (size_t)r * O.ldu + k, F.vecU, nv, v);
+        break;
+    case RSB_OPND_BN_RELU:
+        ld4(O.U + (size_t)r * O.ldu + k, F.vecU, nv, u);
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = fmaxf(fmaf(u[e], c.a[e], c.d[e]), 0.f);
+        break;
+    case RSB_OPND_DUAL_BN_RELU: {
+        float u2[4];
+        ld4(O.U + (size_t)r * O.ldu + k, F.vecU, nv, u);
+        ld4(O.U + (size_t)r * O.ldu + O.ku + k, F.vecU2, nv, u2);
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = fmaxf(fmaf(u[e], c.a[e], c.d[e]) + fmaf(u2[e], c.a2[e], c.d2[e]), 0.f);
+        break;
+    }
+    case RSB_OPND_AFFINE2: {
+        float w[4];
+        ld4(O.U + (size_t)r * O.ldu + (k % O.ku), F.vecU, nv, u);
+        ld4(O.V + (size_t)r * O.ldv + k, F.vecV, nv, w);
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = fmaf(c.a[e], u[e], fmaf(c.b[e], w[e], c.d[e]));
+        break;
+    }
+    default: {  // RSB_OPND_POOLED: dZ is nonzero only on the arg-max sample of its (group, channel)
+        float w[4];
+        ld4(O.V + (size_t)r * O.ldv + k, F.vecV, nv, w);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            float dz = 0.f;
+            if (e < nv && __ldg(O.arg + (size_t)g * O.ldu + k + e) == sidx) dz = __ldg(O.U + (size_t)g * O.ldu + k + e);
+            v[e] = fmaf(c.a[e], dz, fmaf(c.b[e], w[e], c.d[e]));
+        }
+        break;
+    }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) v[e] = e < nv ? v[e] : 0.f;
+}
+
+// one channel k of row r (wgrad staging walks 4 consecutive rows of a fixed channel)
+__device__ __forceinline__ float opnd_eval1(const Opnd &O, long r, int k, float a, float b, float d, float a2, float d2,
+                                            long g, int sidx)
 {
     switch (O.kind) {
     case RSB_OPND_RAW:
         return __ldg(O.U + (size_t)r * O.ldu + k);
     case RSB_OPND_BN_RELU:
-        return fmaxf(fmaf(__ldg(O.U + (size_t)r * O.ldu + k), __ldg(O.a + k), __ldg(O.d + k)), 0.f);
+        return fmaxf(fmaf(__ldg(O.U + (size_t)r * O.ldu + k), a, d), 0.f);
     case RSB_OPND_DUAL_BN_RELU: {
         const float *u = O.U + (size_t)r * O.ldu;
-        const float z = fmaf(__ldg(u + k), __ldg(O.a + k), __ldg(O.d + k)) +
-                        fmaf(__ldg(u + O.ku + k), __ldg(O.a + O.ku + k), __ldg(O.d + O.ku + k));
-        return fmaxf(z, 0.f);
+        return fmaxf(fmaf(__ldg(u + k), a, d) + fmaf(__ldg(u + O.ku + k), a2, d2), 0.f);
     }
-    case RSB_OPND_AFFINE2: {
-        const int ku = k % O.ku;
-        return fmaf(__ldg(O.a + k), __ldg(O.U + (size_t)r * O.ldu + ku),
-                    fmaf(__ldg(O.b + k), __ldg(O.V + (size_t)r * O.ldv + k), __ldg(O.d + k)));
-    }
-    default: {  // RSB_OPND_POOLED: dZ is nonzero only on the arg-max row of its (group, channel)
-        const long g = r / O.ns;
-        const float dz = (__ldg(O.arg + (size_t)g * O.ldu + k) == (int)(r - g * O.ns)) ? __ldg(O.U + (size_t)g * O.ldu + k) : 0.f;
-        return fmaf(__ldg(O.a + k), dz, fmaf(__ldg(O.b + k), __ldg(O.V + (size_t)r * O.ldv + k), __ldg(O.d + k)));
+    case RSB_OPND_AFFINE2:
+        return fmaf(a, __ldg(O.U + (size_t)r * O.ldu + (k % O.ku)), fmaf(b, __ldg(O.V + (size_t)r * O.ldv + k), d));
+    default: {
+        const float dz = (__ldg(O.arg + (size_t)g * O.ldu + k) == sidx) ? __ldg(O.U + (size_t)g * O.ldu + k) : 0.f;
+        return fmaf(a, dz, fmaf(b, __ldg(O.V + (size_t)r * O.ldv + k), d));
     }
     }
 }
@@ -213,11 +304,11 @@ struct Barriers {
 __device__ __forceinline__ uint32_t cta_prologue(Barriers *B, int tid, int warp)
 {
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&B->full[s], 128 + 1); mbar_init(&B->empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&B->full[s], PROD_THREADS + 1); mbar_init(&B->empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&B->acc_full[a], 1); mbar_init(&B->acc_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(rsb_smem_addr(&B->tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -231,7 +322,7 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem_base, int warp)
 {
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
     }
@@ -256,13 +347,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
     const Opnd &A = P.A;
     const Epi &E = P.E;
 
-    if (warp < 4) {
-        // =============================== producers: one thread per row ===============================
-        const int r = tid;
+    if (warp < PROD_WARPS) {
+        // ===== producers: thread = (channel quad k4, row sub-index); 4 rows per thread per chunk, coefficients hoisted
+        const int k4 = tid & 7, rsub = tid >> 3;          // rsub 0..31 -> rows rsub, rsub+32, rsub+64, rsub+96
+        const OpndFlags F = opnd_flags(A);
         uint32_t it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
-            const long row = tile * TM + r;
-            const bool row_ok = row < P.rows;
+            const long row_base = tile * TM;
             for (int nt = 0; nt < P.n_tiles; nt++) {
                 for (int kc = 0; kc < kc_count; kc++, it++) {
                     const int s = it % STAGES;
@@ -276,26 +367,38 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                     }
                     float *a_hi = reinterpret_cast<float *>(st);
                     float *a_lo = reinterpret_cast<float *>(st + A_TILE_BYTES);
-                    const int row_off = (r >> 3) * (KC / 4) * 32 + (r & 7) * 4;  // floats: (r/8)*SBO + (r%8)*16 B
+                    const int kl = kc * KC + k4 * 4;                 // logical channel (without k0)
+                    const int nv = min(4, A.K - kl);                 // valid channels of this quad (<= 0: none)
+                    Coef4 cf;
+                    if (nv > 0) coef_load(A, A.k0 + kl, nv, cf);
+                    float v[4][4];
 #pragma unroll
-                    for (int c4 = 0; c4 < KC / 4; c4++) {
-                        float v[4];
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int k = kc * KC + c4 * 4 + e;
-                            v[e] = (row_ok && k < A.K) ? opnd_load(A, row, A.k0 + k) : 0.f;
+                    for (int j = 0; j < 4; j++) {
+                        const long row = row_base + rsub + 32 * j;
+                        if (nv > 0 && row < P.rows) {
+                            long g = 0;
+                            int sidx = 0;
+                            if (A.kind == RSB_OPND_POOLED) { g = row / A.ns; sidx = (int)(row - g * A.ns); }
+                            opnd_eval4(A, F, cf, row, A.k0 + kl, nv, g, sidx, v[j]);
+                        } else {
+                            v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.f;
                         }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int r = rsub + 32 * j;
                         float4 hi, lo;
-                        split4(v, hi, lo);
-                        *reinterpret_cast<float4 *>(a_hi + row_off + c4 * 32) = hi;
-                        *reinterpret_cast<float4 *>(a_lo + row_off + c4 * 32) = lo;
+                        split4(v[j], hi, lo);
+                        const int off = (r >> 3) * (KC / 4) * 32 + k4 * 32 + (r & 7) * 4;   // floats
+                        *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                        *reinterpret_cast<float4 *>(a_lo + off) = lo;
                     }
                     fence_proxy_async();
                     mbar_arrive(&B->full[s]);
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================
         const uint32_t idesc = umma_idesc_tf32(TM, NT, false);
         uint32_t it = 0, acc_it = 0;
@@ -334,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
         // =============================== epilogue ===============================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;
-        float *my_tile = stat_tile + (warp - 5) * 32 * 33;
+        float *my_tile = stat_tile + (warp - MMA_WARP - 1) * 32 * 33;
         uint32_t acc_it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
             const long row = tile * TM + r;
@@ -349,7 +452,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                     float v[32];
                     tmem_ld32(taddr + c0, v);
                     const int n0 = nt * NT + c0;
-                    float x1[32], x2[32];   // xhat terms for the dgrad statistics (dead code for kind 0)
+                    const float *yl = E.kind == RSB_EPI_RELU_MASK ? E.Yl + (size_t)(row_ok ? row : 0) * E.ldl : nullptr;
                     if (E.kind == RSB_EPI_BIAS_STATS) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
@@ -358,26 +461,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                             v[j] = (row_ok && n < P.N) ? y : 0.f;
                         }
                     } else {
-                        // dgrad: ReLU mask of the layer below from its stored pre-BN output, and xhat for BN backward
-                        const float *yl = E.Yl + (size_t)(row_ok ? row : 0) * E.ldl;
+                        // dgrad: ReLU mask of the layer below, recomputed from its stored pre-BN output
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const int n = n0 + j;
-                            float out = 0.f, h1 = 0.f, h2 = 0.f;
+                            float out = 0.f;
                             if (row_ok && n < P.N) {
-                                const float y1 = __ldg(yl + n);
-                                float z = fmaf(y1, __ldg(E.sc + n), __ldg(E.sh + n));
-                                h1 = (y1 - __ldg(E.mu + n)) * __ldg(E.inv + n);
-                                if (E.dual) {
-                                    const float y2 = __ldg(yl + P.N + n);
-                                    z += fmaf(y2, __ldg(E.sc + P.N + n), __ldg(E.sh + P.N + n));
-                                    h2 = (y2 - __ldg(E.mu + P.N + n)) * __ldg(E.inv + P.N + n);
-                                }
+                                float z = fmaf(__ldg(yl + n), __ldg(E.sc + n), __ldg(E.sh + n));
+                                if (E.dual) z += fmaf(__ldg(yl + P.N + n), __ldg(E.sc + P.N + n), __ldg(E.sh + P.N + n));
                                 out = z > 0.f ? v[j] : 0.f;
                             }
                             v[j] = out;
-                            x1[j] = out * h1;
-                            x2[j] = out * h2;
                         }
                     }
                     if (row_ok && E.Y) {
@@ -391,26 +485,40 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                         }
                     }
                     if (E.stats) {
+                        // column sums over this warp's 32 rows through a padded shared tile, then fp64 atomics
                         const int n = n0 + lane;
+                        const float s0 = warp_colsum(my_tile, v, lane);
+                        if (n < P.N) atomicAdd(E.stats + n, (double)s0);
                         if (E.kind == RSB_EPI_BIAS_STATS) {
-                            float sq[32];
 #pragma unroll
-                            for (int j = 0; j < 32; j++) sq[j] = v[j] * v[j];
-                            const float s1 = warp_colsum(my_tile, v, lane), s2 = warp_colsum(my_tile, sq, lane);
-                            if (n < P.N) {
-                                atomicAdd(E.stats + n, (double)s1);
-                                atomicAdd(E.stats + P.N + n, (double)s2);
-                            }
+                            for (int j = 0; j < 32; j++) my_tile[lane * 33 + j] = v[j] * v[j];
                         } else {
-                            const float s0 = warp_colsum(my_tile, v, lane), s1 = warp_colsum(my_tile, x1, lane);
-                            if (n < P.N) {
-                                atomicAdd(E.stats + n, (double)s0);
-                                atomicAdd(E.stats + P.N + n, (double)s1);
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const int nn = n0 + j;
+                                const float h = (row_ok && nn < P.N) ? (__ldg(yl + nn) - __ldg(E.mu + nn)) * __ldg(E.inv + nn) : 0.f;
+                                my_tile[lane * 33 + j] = v[j] * h;
                             }
-                            if (E.dual) {
-                                const float s2 = warp_colsum(my_tile, x2, lane);
-                                if (n < P.N) atomicAdd(E.stats + 2 * P.N + n, (double)s2);
+                        }
+                        __syncwarp();
+                        float s1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) s1 += my_tile[i * 33 + lane];
+                        __syncwarp();
+                        if (n < P.N) atomicAdd(E.stats + P.N + n, (double)s1);
+                        if (E.kind == RSB_EPI_RELU_MASK && E.dual) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const int nn = n0 + j;
+                                const float h = (row_ok && nn < P.N) ? (__ldg(yl + P.N + nn) - __ldg(E.mu + P.N + nn)) * __ldg(E.inv + P.N + nn) : 0.f;
+                                my_tile[lane * 33 + j] = v[j] * h;
                             }
+                            __syncwarp();
+                            float s2 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; i++) s2 += my_tile[i * 33 + lane];
+                            __syncwarp();
+                            if (n < P.N) atomicAdd(E.stats + 2 * P.N + n, (double)s2);
                         }
                     }
                 }
@@ -428,25 +536,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
 // Stage the TRANSPOSE of a [32 rows x width channels] slab as a K-major tile (channels = tile rows, the 32
 // reduction rows = K): lanes run along channels (coalesced global reads of one slab row), each thread packs 4
 // consecutive reduction rows of its channel into one 16 B core-matrix row.  Same canonical layout and
-// descriptors as gemm_rows (LBO 128 B, SBO 1024 B).
+// descriptors as gemm_rows (LBO 128 B, SBO 1024 B).  8 warps: warp w takes the row quad k4 = w.
 __device__ __forceinline__ void wgrad_stage_operand(const Opnd &O, int width, int c_base, long row0, long rows,
                                                     float *hi_base, float *lo_base, int warp, int lane)
 {
-    for (int k4 = warp; k4 < KC / 4; k4 += 4) {
-        const long r0 = row0 + k4 * 4;
-        for (int cb = 0; cb < width; cb += 32) {
-            const int ct = cb + lane;            // channel inside the tile
-            if (ct >= width) break;              // tiles are multiples of 16 channels, not of 32
-            const int c = c_base + ct;           // logical channel of the operand
-            float v[4];
+    const int k4 = warp;                     // PROD_WARPS == KC / 4
+    const long r0 = row0 + k4 * 4;
+    long g[4] = {0, 0, 0, 0};
+    int sidx[4] = {0, 0, 0, 0};
+    if (O.kind == RSB_OPND_POOLED) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) v[e] = (r0 + e < rows && c < O.K) ? opnd_load(O, r0 + e, O.k0 + c) : 0.f;
-            float4 hi, lo;
-            split4(v, hi, lo);
-            const int off = (ct >> 3) * (KC / 4) * 32 + k4 * 32 + (ct & 7) * 4;   // floats
-            *reinterpret_cast<float4 *>(hi_base + off) = hi;
-            *reinterpret_cast<float4 *>(lo_base + off) = lo;
+        for (int e = 0; e < 4; e++) { g[e] = (r0 + e) / O.ns; sidx[e] = (int)(r0 + e - g[e] * O.ns); }
+    }
+    for (int cb = 0; cb < width; cb += 32) {
+        const int ct = cb + lane;            // channel inside the tile
+        if (ct >= width) break;              // tiles are multiples of 16 channels, not of 32
+        const int c = c_base + ct;           // logical channel of the operand
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < O.K) {
+            const int k = O.k0 + c;
+            const float a = O.a ? __ldg(O.a + k) : 0.f, d = O.d ? __ldg(O.d + k) : 0.f, b = O.b ? __ldg(O.b + k) : 0.f;
+            float a2 = 0.f, d2 = 0.f;
+            if (O.kind == RSB_OPND_DUAL_BN_RELU) { a2 = __ldg(O.a + O.ku + k); d2 = __ldg(O.d + O.ku + k); }
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (r0 + e < rows) v[e] = opnd_eval1(O, r0 + e, k, a, b, d, a2, d2, g[e], sidx[e]);
         }
+        float4 hi, lo;
+        split4(v, hi, lo);
+        const int off = (ct >> 3) * (KC / 4) * 32 + k4 * 32 + (ct & 7) * 4;   // floats
+        *reinterpret_cast<float4 *>(hi_base + off) = hi;
+        *reinterpret_cast<float4 *>(lo_base + off) = lo;
     }
 }
 
@@ -466,7 +586,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     const long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (my_chunks > 0) {
-        if (warp < 4) {
+        if (warp < PROD_WARPS) {
             uint32_t it = 0;
             for (int mt = 0; mt < P.m_tiles; mt++)
                 for (int nt = 0; nt < P.n_tiles; nt++)
@@ -481,9 +601,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                                             reinterpret_cast<float *>(st + 2 * a_bytes + b_bytes), warp, lane);
                         fence_proxy_async();
                         mbar_arrive(&B->full[s]);
-                        if (tid == 0) mbar_arrive(&B->full[s]);   // barrier counts 129 (shared with gemm_rows)
+                        if (tid == 0) mbar_arrive(&B->full[s]);   // barrier counts PROD_THREADS + 1 (shared with gemm_rows)
                     }
-        } else if (warp == 4) {
+        } else if (warp == MMA_WARP) {
             const uint32_t idesc = umma_idesc_tf32(TM, NT, false);
             uint32_t it = 0, acc_it = 0;
             for (int mt = 0; mt < P.m_tiles; mt++)

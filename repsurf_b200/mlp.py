@@ -27,6 +27,17 @@ def bn_rows(x, bn):
                         0.0 if bn.momentum is None else bn.momentum, bn.eps)
 
 
+def sa_mlp(rows, pos_channel, mod, nsample):
+    """Shared MLP + max-pool of a SurfaceAbstractionCD level.  Training mode runs the fused tcgen05 path
+    (repsurf_b200.tc: 3xTF32 GEMMs with BatchNorm/ReLU/pool folded into operand loads and epilogues, hand-written
+    backward); eval mode (running statistics, no autograd through BatchNorm statistics) uses the row-matrix
+    composition below."""
+    if mod.training and rows.is_cuda and len(mod.mlp_convs) >= 1:
+        from . import tc
+        return tc.sa_mlp_fused(rows, pos_channel, mod, nsample)
+    return sa_mlp_rows(rows, pos_channel, mod, nsample)
+
+
 def sa_mlp_rows(rows, pos_channel, mod, nsample):
     """Channel-de-differentiated shared MLP + max-pool.  rows [G*nsample, C] -> [G, mlp[-1]].
     mod provides mlp_l0/mlp_f0/bn_l0/bn_f0/mlp_convs/mlp_bns (the reference's attribute names)."""

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import pointops as P
 from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, linear_rows, sa_mlp_rows
+from ..mlp import bn_rows, linear_rows, sa_mlp
 
 
 def strided_offsets(offset, stride):
@@ -87,7 +87,7 @@ class SurfaceAbstractionCD(nn.Module):
             self.stride, self.nsample, center, normal, feature, offset, self.return_polar, self.num_sector,
             self.training)
         M, ns, C = x.shape
-        return [new_center, new_normal, sa_mlp_rows(x.view(M * ns, C), self.pos_channel, self, ns), new_offset]
+        return [new_center, new_normal, sa_mlp(x.view(M * ns, C), self.pos_channel, self, ns), new_offset]
 
 
 class SurfaceFeaturePropagationCD(nn.Module):
