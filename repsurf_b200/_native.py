@@ -46,6 +46,7 @@ _SIGS = {
     "rsb_pool_forward": [_l, _i, _i, _p, _i, _p, _p, _p, _p],
     "rsb_pool_backward_stats": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "rsb_bn_backward_coef": [_i, _l, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rsb_bn_relu_backward": [_l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
                                 "rsb_linear_tc_weight_floats"])

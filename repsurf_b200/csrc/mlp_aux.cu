@@ -104,7 +104,90 @@ __global__ void bn_bwd_coef_kernel(int C, double rows, const double *__restrict_
     }
 }
 
+// dZ = dA where the layer's activation was positive (z = sc*Y + sh [+ second BatchNorm half] > 0), in place;
+// stats += (sum dZ, sum dZ*xhat_1 [, sum dZ*xhat_2]) per channel.  Thread = one channel quad, grid-stride over
+// rows: coalesced 16-byte accesses, register accumulation, one shared-memory reduction + fp64 atomics per block.
+__global__ void __launch_bounds__(256) bn_relu_bwd_kernel(long rows, int C, float *__restrict__ dA, int ldd,
+                                                          const float *__restrict__ Y, int ldy,
+                                                          const float *__restrict__ sc, const float *__restrict__ sh,
+                                                          const float *__restrict__ mu, const float *__restrict__ inv,
+                                                          int dual, double *__restrict__ stats, int rows_per_block)
+{
+    const int quads = C / 4;                         // C % 4 == 0 (checked by the launcher)
+    const int q = threadIdx.x % quads;               // blockDim.x is a multiple of quads
+    const int rlane = threadIdx.x / quads, rstep = blockDim.x / quads;
+    const int c = q * 4;
+    const float4 a1 = *reinterpret_cast<const float4 *>(sc + c), b1 = *reinterpret_cast<const float4 *>(sh + c);
+    const float4 m1 = *reinterpret_cast<const float4 *>(mu + c), i1 = *reinterpret_cast<const float4 *>(inv + c);
+    float4 a2 = make_float4(0, 0, 0, 0), b2 = a2, m2 = a2, i2 = a2;
+    if (dual) {
+        a2 = *reinterpret_cast<const float4 *>(sc + C + c); b2 = *reinterpret_cast<const float4 *>(sh + C + c);
+        m2 = *reinterpret_cast<const float4 *>(mu + C + c); i2 = *reinterpret_cast<const float4 *>(inv + C + c);
+    }
+    float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const long r0 = (long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (long r = r0 + rlane; r < r1; r += rstep) {
+        float4 d = *reinterpret_cast<float4 *>(dA + (size_t)r * ldd + c);
+        const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + (size_t)r * ldy + c));
+        float4 y2 = make_float4(0, 0, 0, 0);
+        float z[4] = {fmaf(y.x, a1.x, b1.x), fmaf(y.y, a1.y, b1.y), fmaf(y.z, a1.z, b1.z), fmaf(y.w, a1.w, b1.w)};
+        if (dual) {
+            y2 = __ldg(reinterpret_cast<const float4 *>(Y + (size_t)r * ldy + C + c));
+            z[0] += fmaf(y2.x, a2.x, b2.x); z[1] += fmaf(y2.y, a2.y, b2.y); z[2] += fmaf(y2.z, a2.z, b2.z); z[3] += fmaf(y2.w, a2.w, b2.w);
+        }
+        d.x = z[0] > 0.f ? d.x : 0.f; d.y = z[1] > 0.f ? d.y : 0.f; d.z = z[2] > 0.f ? d.z : 0.f; d.w = z[3] > 0.f ? d.w : 0.f;
+        *reinterpret_cast<float4 *>(dA + (size_t)r * ldd + c) = d;
+        s0[0] += d.x; s0[1] += d.y; s0[2] += d.z; s0[3] += d.w;
+        s1[0] = fmaf(d.x, (y.x - m1.x) * i1.x, s1[0]); s1[1] = fmaf(d.y, (y.y - m1.y) * i1.y, s1[1]);
+        s1[2] = fmaf(d.z, (y.z - m1.z) * i1.z, s1[2]); s1[3] = fmaf(d.w, (y.w - m1.w) * i1.w, s1[3]);
+        if (dual) {
+            s2[0] = fmaf(d.x, (y2.x - m2.x) * i2.x, s2[0]); s2[1] = fmaf(d.y, (y2.y - m2.y) * i2.y, s2[1]);
+            s2[2] = fmaf(d.z, (y2.z - m2.z) * i2.z, s2[2]); s2[3] = fmaf(d.w, (y2.w - m2.w) * i2.w, s2[3]);
+        }
+    }
+    // block reduction over the row lanes that share a channel quad
+    __shared__ float red[3][256][4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) { red[0][threadIdx.x][e] = s0[e]; red[1][threadIdx.x][e] = s1[e]; red[2][threadIdx.x][e] = s2[e]; }
+    __syncthreads();
+    if (rlane == 0) {
+        double t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+        for (int j = 0; j < rstep; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) { t0[e] += red[0][j * quads + q][e]; t1[e] += red[1][j * quads + q][e]; t2[e] += red[2][j * quads + q][e]; }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            atomicAdd(stats + c + e, t0[e]);
+            atomicAdd(stats + C + c + e, t1[e]);
+            if (dual) atomicAdd(stats + 2 * C + c + e, t2[e]);
+        }
+    }
+}
+
 }  // namespace
+
+RSB_EXPORT int rsb_bn_relu_backward(long rows, int C, float *dA, int ldd, const float *Y, int ldy, const float *sc,
+                                    const float *sh, const float *mu, const float *inv, int dual, double *stats,
+                                    cudaStream_t stream)
+{
+    RSB_REQUIRE(C >= 4 && C % 4 == 0 && C <= 1024 && ldd % 4 == 0 && ldy % 4 == 0, "channels / pitches must be multiples of 4");
+    RSB_REQUIRE(((uintptr_t)dA % 16 == 0) && ((uintptr_t)Y % 16 == 0), "tensors must be 16-byte aligned");
+    if (rows == 0) return 0;
+    const int quads = C / 4;
+    int threads = 256;
+    if (quads > 256) threads = quads;                        // C up to 1024: one row lane
+    else threads = (256 / quads) * quads;
+    const int target_blocks = rsb_sm_count() * 8;
+    long rpb = (rows + target_blocks - 1) / target_blocks;
+    const long min_rpb = (long)(threads / quads) * 8;
+    if (rpb < min_rpb) rpb = min_rpb;
+    const int blocks = (int)((rows + rpb - 1) / rpb);
+    RSB_REQUIRE(threads <= 256, "too many channels");
+    bn_relu_bwd_kernel<<<blocks, threads, 0, stream>>>(rows, C, dA, ldd, Y, ldy, sc, sh, mu, inv, dual, stats, (int)rpb);
+    RSB_CHECK_LAUNCH("bn_relu_bwd_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
 
 RSB_EXPORT int rsb_bn_finalize(int C, long rows, const double *stats, const float *gamma, const float *beta, float eps,
                                float momentum, float *running_mean, float *running_var, float *sc, float *sh,

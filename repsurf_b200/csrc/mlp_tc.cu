@@ -33,10 +33,11 @@ namespace {
 
 constexpr int TM = 128;          // UMMA M
 constexpr int KC = 32;           // reduction elements per pipeline chunk (4 UMMA k-steps of 8)
-constexpr int STAGES = 2;
+constexpr int STAGES_MAX = 4;     // pipeline depth is chosen per launch from the shared-memory budget
 constexpr int NT_MAX = 256;      // UMMA N <= 256
 constexpr int A_TILE_BYTES = TM * KC * 4;           // 16 KB (one of hi / lo), K-major tiles
-constexpr int PROD_WARPS = 8;                      // operand-staging warps
+constexpr int PROD_WARPS = 8;                      // operand-staging warps: two groups of 4, alternating chunks
+constexpr int GROUP_THREADS = 128;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int MMA_WARP = PROD_WARPS;               // warp index of the MMA issuer
 constexpr int THREADS = (PROD_WARPS + 1 + 4) * 32; // + 4 epilogue warps
@@ -49,7 +50,8 @@ struct RowsParams {
     Epi E;
     const float *Wp;
     long rows;
-    int N, NT, n_tiles, k_chunks;
+    int N, NT, n_tiles, k_chunks, stages;
+    int raw_depth;   // > 0: operand pieces are prefetched with cp.async into a per-thread ring of this depth
 };
 
 struct WgradParams {
@@ -57,7 +59,7 @@ struct WgradParams {
     float *dW;
     int ldw;
     long rows;
-    int M, N, NT, m_tiles, n_tiles;
+    int M, N, NT, m_tiles, n_tiles, stages;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -208,40 +210,29 @@ __device__ __forceinline__ OpndFlags opnd_flags(const Opnd &O)
     return f;
 }
 
-// 4 consecutive channels k..k+3 (k includes k0, k % 4 == 0 relative to k0) of row r; nv = valid channels.
-// (g, sidx) = pooling group of r and its sample index inside the group (POOLED only).
-__device__ __forceinline__ void opnd_eval4(const Opnd &O, const OpndFlags &F, const Coef4 &c, long r, int k, int nv,
-                                           long g, int sidx, float *v)
+// Math of the operand transform on already-fetched quads: u = first piece, w = second piece
+// (DUAL: the second half of U; AFFINE2 / POOLED: V).  POOLED additionally reads the pooled gradient.
+__device__ __forceinline__ void opnd_apply4(const Opnd &O, const Coef4 &c, const float *u, const float *w, int k, int nv,
+                                            long g, int sidx, float *v)
 {
-    float u[4];
     switch (O.kind) {
     case RSB_OPND_RAW:
-        ld4(O.U + (size_t)r * O.ldu + k, F.vecU, nv, v);
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = u[e];
         break;
     case RSB_OPND_BN_RELU:
-        ld4(O.U + (size_t)r * O.ldu + k, F.vecU, nv, u);
 #pragma unroll
         for (int e = 0; e < 4; e++) v[e] = fmaxf(fmaf(u[e], c.a[e], c.d[e]), 0.f);
         break;
-    case RSB_OPND_DUAL_BN_RELU: {
-        float u2[4];
-        ld4(O.U + (size_t)r * O.ldu + k, F.vecU, nv, u);
-        ld4(O.U + (size_t)r * O.ldu + O.ku + k, F.vecU2, nv, u2);
+    case RSB_OPND_DUAL_BN_RELU:
 #pragma unroll
-        for (int e = 0; e < 4; e++) v[e] = fmaxf(fmaf(u[e], c.a[e], c.d[e]) + fmaf(u2[e], c.a2[e], c.d2[e]), 0.f);
+        for (int e = 0; e < 4; e++) v[e] = fmaxf(fmaf(u[e], c.a[e], c.d[e]) + fmaf(w[e], c.a2[e], c.d2[e]), 0.f);
         break;
-    }
-    case RSB_OPND_AFFINE2: {
-        float w[4];
-        ld4(O.U + (size_t)r * O.ldu + (k % O.ku), F.vecU, nv, u);
-        ld4(O.V + (size_t)r * O.ldv + k, F.vecV, nv, w);
+    case RSB_OPND_AFFINE2:
 #pragma unroll
         for (int e = 0; e < 4; e++) v[e] = fmaf(c.a[e], u[e], fmaf(c.b[e], w[e], c.d[e]));
         break;
-    }
-    default: {  // RSB_OPND_POOLED: dZ is nonzero only on the arg-max sample of its (group, channel)
-        float w[4];
-        ld4(O.V + (size_t)r * O.ldv + k, F.vecV, nv, w);
+    default:  // RSB_OPND_POOLED: dZ is nonzero only on the arg-max sample of its (group, channel)
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             float dz = 0.f;
@@ -250,10 +241,53 @@ __device__ __forceinline__ void opnd_eval4(const Opnd &O, const OpndFlags &F, co
         }
         break;
     }
-    }
 #pragma unroll
     for (int e = 0; e < 4; e++) v[e] = e < nv ? v[e] : 0.f;
 }
+
+// global addresses of the (up to) two 16-byte pieces a quad needs
+__device__ __forceinline__ void opnd_pieces(const Opnd &O, long r, int k, const float *&p0, const float *&p1)
+{
+    p0 = p1 = nullptr;
+    switch (O.kind) {
+    case RSB_OPND_RAW:
+    case RSB_OPND_BN_RELU:
+        p0 = O.U + (size_t)r * O.ldu + k;
+        break;
+    case RSB_OPND_DUAL_BN_RELU:
+        p0 = O.U + (size_t)r * O.ldu + k;
+        p1 = p0 + O.ku;
+        break;
+    case RSB_OPND_AFFINE2:
+        p0 = O.U + (size_t)r * O.ldu + (k % O.ku);
+        p1 = O.V + (size_t)r * O.ldv + k;
+        break;
+    default:
+        p1 = O.V + (size_t)r * O.ldv + k;
+        break;
+    }
+}
+
+// 4 consecutive channels k..k+3 (k includes k0) of row r; nv = valid channels (synchronous fetch).
+__device__ __forceinline__ void opnd_eval4(const Opnd &O, const OpndFlags &F, const Coef4 &c, long r, int k, int nv,
+                                           long g, int sidx, float *v)
+{
+    const float *p0, *p1;
+    opnd_pieces(O, r, k, p0, p1);
+    float u[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p0) ld4(p0, F.vecU, nv, u);
+    if (p1) ld4(p1, O.kind == RSB_OPND_DUAL_BN_RELU ? F.vecU2 : F.vecV, nv, w);
+    opnd_apply4(O, c, u, w, k, nv, g, sidx, v);
+}
+
+// 16-byte asynchronous global->shared copy; bytes beyond src_bytes are zero-filled (src_bytes may be 0)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(rsb_smem_addr(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // one channel k of row r (wgrad staging walks 4 consecutive rows of a fixed channel)
 __device__ __forceinline__ float opnd_eval1(const Opnd &O, long r, int k, float a, float b, float d, float a2, float d2,
@@ -296,15 +330,15 @@ __device__ __forceinline__ float warp_colsum(float *tile, const float *v, int la
     return s;
 }
 
-struct Barriers {
-    uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+struct alignas(128) Barriers {
+    uint64_t full[STAGES_MAX], empty[STAGES_MAX], acc_full[2], acc_empty[2];
     uint32_t tmem_slot, pad;
 };
 
-__device__ __forceinline__ uint32_t cta_prologue(Barriers *B, int tid, int warp)
+__device__ __forceinline__ uint32_t cta_prologue(Barriers *B, int tid, int warp, int full_count = GROUP_THREADS + 1)
 {
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&B->full[s], PROD_THREADS + 1); mbar_init(&B->empty[s], 1); }
+        for (int s = 0; s < STAGES_MAX; s++) { mbar_init(&B->full[s], full_count); mbar_init(&B->empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&B->acc_full[a], 1); mbar_init(&B->acc_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -338,9 +372,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
     const int NT = P.NT;
     const size_t b_bytes = (size_t)NT * KC * 4;  // one of hi / lo
     const size_t stage_bytes = 2 * A_TILE_BYTES + 2 * b_bytes;
+    const int STAGES = P.stages;
     Barriers *B = reinterpret_cast<Barriers *>(smem + STAGES * stage_bytes);
-    float *stat_tile = reinterpret_cast<float *>(B + 1);  // [4 warps][32][33]
-    const uint32_t tmem_base = cta_prologue(B, tid, warp);
+    float *stat_tile = reinterpret_cast<float *>(B + 1);  // [4 warps][32][33], then the cp.async ring
+    const uint32_t tmem_base = cta_prologue(B, tid, warp, P.raw_depth > 0 ? PROD_THREADS + 1 : GROUP_THREADS + 1);
 
     const long n_row_tiles = (P.rows + TM - 1) / TM;
     const int kc_count = P.k_chunks;
@@ -348,19 +383,101 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
     const Epi &E = P.E;
 
     if (warp < PROD_WARPS) {
-        // ===== producers: thread = (channel quad k4, row sub-index); 4 rows per thread per chunk, coefficients hoisted
-        const int k4 = tid & 7, rsub = tid >> 3;          // rsub 0..31 -> rows rsub, rsub+32, rsub+64, rsub+96
+        if (P.raw_depth > 0) {
+            // ===== producers, asynchronous path: every thread owns 4 rows x one channel quad of each chunk and
+            // prefetches its own 16-byte pieces RD chunks ahead with cp.async into a private shared-memory ring
+            // (no registers held, no cross-thread hand-off), so ~RD * 32 KB per SM are always in flight.
+            constexpr int RD_MAX = 3;
+            const int RD = P.raw_depth;
+            float4 *ring = reinterpret_cast<float4 *>(stat_tile + 4 * 32 * 33);       // [RD][2 pieces][4 rows][256 threads]
+            const int k4 = tid & 7, rsub = tid >> 3;                                   // rows rsub + 32*j
+            const long my_tiles = n_row_tiles > blockIdx.x ? (n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const int per_tile = P.n_tiles * kc_count;
+            const long total = my_tiles * per_tile;
+            auto issue = [&](long q) {
+                if (q < total) {
+                    const long ti = q / per_tile;
+                    const int kc = (int)(q - ti * per_tile) % kc_count;
+                    const long row_base = (blockIdx.x + ti * gridDim.x) * (long)TM;
+                    const int kl = kc * KC + k4 * 4;
+                    const int nv = min(4, A.K - kl);
+                    float4 *slot = ring + (size_t)(q % RD) * (2 * 4 * PROD_THREADS);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const long row = row_base + rsub + 32 * j;
+                        const bool ok = nv > 0 && row < P.rows;
+                        const float *p0, *p1;
+                        opnd_pieces(A, ok ? row : 0, A.k0 + (nv > 0 ? kl : 0), p0, p1);
+                        if (p0) cp_async16(slot + (0 * 4 + j) * PROD_THREADS + tid, p0, ok ? nv * 4 : 0);
+                        if (p1) cp_async16(slot + (1 * 4 + j) * PROD_THREADS + tid, p1, ok ? nv * 4 : 0);
+                    }
+                }
+                cp_async_commit();
+            };
+            for (int p = 0; p < RD; p++) issue(p);
+            for (long q = 0; q < total; q++) {
+                const uint32_t it = (uint32_t)q;
+                const long ti = q / per_tile;
+                const int rem = (int)(q - ti * per_tile);
+                const int nt = rem / kc_count, kc = rem % kc_count;
+                const long row_base = (blockIdx.x + ti * gridDim.x) * (long)TM;
+                const int s = it % STAGES;
+                if (RD == 3) cp_async_wait<RD_MAX - 1>(); else if (RD == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+                mbar_wait(&B->empty[s], ((it / STAGES) & 1) ^ 1);
+                unsigned char *st = smem + (size_t)s * stage_bytes;
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&B->full[s], (uint32_t)(2 * b_bytes));
+                    const float *src = P.Wp + ((size_t)nt * kc_count + kc) * (2 * (size_t)NT * KC);
+                    bulk_g2s(st + 2 * A_TILE_BYTES, src, (uint32_t)(2 * b_bytes), &B->full[s]);
+                }
+                float *a_hi = reinterpret_cast<float *>(st);
+                float *a_lo = reinterpret_cast<float *>(st + A_TILE_BYTES);
+                const int kl = kc * KC + k4 * 4;
+                const int nv = min(4, A.K - kl);
+                Coef4 cf;
+                if (nv > 0) coef_load(A, A.k0 + kl, nv, cf);
+                const float4 *slot = ring + (size_t)(q % RD) * (2 * 4 * PROD_THREADS);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int r = rsub + 32 * j;
+                    const long row = row_base + r;
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (nv > 0 && row < P.rows) {
+                        const float4 u4 = slot[(0 * 4 + j) * PROD_THREADS + tid], w4 = slot[(1 * 4 + j) * PROD_THREADS + tid];
+                        const float u[4] = {u4.x, u4.y, u4.z, u4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+                        long g = 0;
+                        int sidx = 0;
+                        if (A.kind == RSB_OPND_POOLED) { g = row / A.ns; sidx = (int)(row - g * A.ns); }
+                        opnd_apply4(A, cf, u, w, A.k0 + kl, nv, g, sidx, v);
+                    }
+                    float4 hi, lo;
+                    split4(v, hi, lo);
+                    const int off = (r >> 3) * (KC / 4) * 32 + k4 * 32 + (r & 7) * 4;   // floats
+                    *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                    *reinterpret_cast<float4 *>(a_lo + off) = lo;
+                }
+                fence_proxy_async();
+                mbar_arrive(&B->full[s]);
+                issue(q + RD);
+            }
+            cp_async_wait<0>();
+        } else {
+        // ===== producers: two groups of 4 warps take alternate chunks, so two stages are being loaded at any time.
+        // Inside a group: thread = (channel quad k4, row sub-index), 8 rows per thread per chunk, coefficients hoisted.
+        const int grp = warp >> 2, gt = tid & (GROUP_THREADS - 1);
+        const int k4 = gt & 7, rsub = gt >> 3;            // rsub 0..15 -> rows rsub + 16*j
         const OpndFlags F = opnd_flags(A);
         uint32_t it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
             const long row_base = tile * TM;
             for (int nt = 0; nt < P.n_tiles; nt++) {
                 for (int kc = 0; kc < kc_count; kc++, it++) {
+                    if ((it & 1) != (uint32_t)grp) continue;
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&B->empty[s], ph ^ 1);
                     unsigned char *st = smem + (size_t)s * stage_bytes;
-                    if (tid == 0) {
+                    if (gt == 0) {
                         mbar_arrive_expect_tx(&B->full[s], (uint32_t)(2 * b_bytes));
                         const float *src = P.Wp + ((size_t)nt * kc_count + kc) * (2 * (size_t)NT * KC);
                         bulk_g2s(st + 2 * A_TILE_BYTES, src, (uint32_t)(2 * b_bytes), &B->full[s]);
@@ -371,32 +488,36 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                     const int nv = min(4, A.K - kl);                 // valid channels of this quad (<= 0: none)
                     Coef4 cf;
                     if (nv > 0) coef_load(A, A.k0 + kl, nv, cf);
-                    float v[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const long row = row_base + rsub + 32 * j;
-                        if (nv > 0 && row < P.rows) {
-                            long g = 0;
-                            int sidx = 0;
-                            if (A.kind == RSB_OPND_POOLED) { g = row / A.ns; sidx = (int)(row - g * A.ns); }
-                            opnd_eval4(A, F, cf, row, A.k0 + kl, nv, g, sidx, v[j]);
-                        } else {
-                            v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.f;
+                    for (int half = 0; half < 2; half++) {
+                        float v[4][4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const long row = row_base + rsub + 16 * (half * 4 + j);
+                            if (nv > 0 && row < P.rows) {
+                                long g = 0;
+                                int sidx = 0;
+                                if (A.kind == RSB_OPND_POOLED) { g = row / A.ns; sidx = (int)(row - g * A.ns); }
+                                opnd_eval4(A, F, cf, row, A.k0 + kl, nv, g, sidx, v[j]);
+                            } else {
+                                v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.f;
+                            }
                         }
-                    }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int r = rsub + 32 * j;
-                        float4 hi, lo;
-                        split4(v[j], hi, lo);
-                        const int off = (r >> 3) * (KC / 4) * 32 + k4 * 32 + (r & 7) * 4;   // floats
-                        *reinterpret_cast<float4 *>(a_hi + off) = hi;
-                        *reinterpret_cast<float4 *>(a_lo + off) = lo;
+                        for (int j = 0; j < 4; j++) {
+                            const int r = rsub + 16 * (half * 4 + j);
+                            float4 hi, lo;
+                            split4(v[j], hi, lo);
+                            const int off = (r >> 3) * (KC / 4) * 32 + k4 * 32 + (r & 7) * 4;   // floats
+                            *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                            *reinterpret_cast<float4 *>(a_lo + off) = lo;
+                        }
                     }
                     fence_proxy_async();
                     mbar_arrive(&B->full[s]);
                 }
             }
+        }
         }
     } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================
@@ -438,6 +559,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;
         float *my_tile = stat_tile + (warp - MMA_WARP - 1) * 32 * 33;
+        // forward statistics live in registers for the whole kernel (column n0 + lane of every 32-column block of
+        // every N tile this thread sees); one fp64 atomic per (CTA warp, column) at the end instead of per tile
+        constexpr int ACC_BLOCKS = NT_MAX / 32;
+        double acc1[ACC_BLOCKS], acc2[ACC_BLOCKS];
+#pragma unroll
+        for (int i = 0; i < ACC_BLOCKS; i++) acc1[i] = acc2[i] = 0.0;
+        const bool reg_stats = E.stats && E.kind == RSB_EPI_BIAS_STATS && P.n_tiles == 1;
         uint32_t acc_it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
             const long row = tile * TM + r;
@@ -488,6 +616,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                         // column sums over this warp's 32 rows through a padded shared tile, then fp64 atomics
                         const int n = n0 + lane;
                         const float s0 = warp_colsum(my_tile, v, lane);
+                        if (reg_stats) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) my_tile[lane * 33 + j] = v[j] * v[j];
+                            __syncwarp();
+                            float sq = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; i++) sq += my_tile[i * 33 + lane];
+                            __syncwarp();
+#pragma unroll
+                            for (int bi = 0; bi < ACC_BLOCKS; bi++)
+                                if (bi == (c0 >> 5)) { acc1[bi] += (double)s0; acc2[bi] += (double)sq; }
+                            continue;
+                        }
                         if (n < P.N) atomicAdd(E.stats + n, (double)s0);
                         if (E.kind == RSB_EPI_BIAS_STATS) {
 #pragma unroll
@@ -526,6 +667,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                 mbar_arrive(&B->acc_empty[ab]);
             }
         }
+        if (reg_stats) {
+#pragma unroll
+            for (int bi = 0; bi < ACC_BLOCKS; bi++) {
+                const int n = bi * 32 + lane;
+                if (n < P.N && (acc1[bi] != 0.0 || acc2[bi] != 0.0)) {
+                    atomicAdd(E.stats + n, acc1[bi]);
+                    atomicAdd(E.stats + P.N + n, acc2[bi]);
+                }
+            }
+        }
     }
     cta_epilogue(tmem_base, warp);
 }
@@ -533,41 +684,88 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
 // ============================================================================================================
 // dW[m, n] += sum_r G(r, m) * X(r, n)   (weight gradient; reduction over rows)
 // ============================================================================================================
-// Stage the TRANSPOSE of a [32 rows x width channels] slab as a K-major tile (channels = tile rows, the 32
+// ---- wgrad staging -------------------------------------------------------------------------------------------
+// The TRANSPOSE of a [32 rows x width channels] slab is staged as a K-major tile (channels = tile rows, the 32
 // reduction rows = K): lanes run along channels (coalesced global reads of one slab row), each thread packs 4
-// consecutive reduction rows of its channel into one 16 B core-matrix row.  Same canonical layout and
-// descriptors as gemm_rows (LBO 128 B, SBO 1024 B).  8 warps: warp w takes the row quad k4 = w.
-__device__ __forceinline__ void wgrad_stage_operand(const Opnd &O, int width, int c_base, long row0, long rows,
-                                                    float *hi_base, float *lo_base, int warp, int lane)
+// consecutive reduction rows of its channel into one 16 B core-matrix row.  Same canonical layout and descriptors
+// as gemm_rows (LBO 128 B, SBO 1024 B).  A "unit" = (operand, 32-channel block, row quad); a group of 4 warps
+// stages one chunk: warp w4 owns the row quads w4 and w4+4.  Units are processed in batches whose global loads
+// are all issued before any is consumed (the kernel is load-latency bound, see profiles/).
+struct WUnit {
+    float u[4], w[4];        // raw pieces of the 4 rows (first / second tensor)
+    float dz[4];             // POOLED: selected pooled gradient per row
+    float a, b, d, a2, d2;   // channel coefficients
+    int ct, k4, which;       // channel inside the tile, row quad, operand (0 = G, 1 = X)
+    bool live;               // channel valid
+};
+
+__device__ __forceinline__ void wunit_load(WUnit &U, const Opnd &O, int c_base, int cb, int k4, long row0, long rows, int lane)
 {
-    const int k4 = warp;                     // PROD_WARPS == KC / 4
+    U.k4 = k4;
+    U.ct = cb + lane;
+    const int c = c_base + U.ct;
+    U.live = c < O.K;
+#pragma unroll
+    for (int e = 0; e < 4; e++) { U.u[e] = 0.f; U.w[e] = 0.f; U.dz[e] = 0.f; }
+    U.a = U.b = U.d = U.a2 = U.d2 = 0.f;
+    if (!U.live) return;
+    const int k = O.k0 + c;
     const long r0 = row0 + k4 * 4;
-    long g[4] = {0, 0, 0, 0};
-    int sidx[4] = {0, 0, 0, 0};
-    if (O.kind == RSB_OPND_POOLED) {
+    if (O.a) U.a = __ldg(O.a + k);
+    if (O.d) U.d = __ldg(O.d + k);
+    if (O.b) U.b = __ldg(O.b + k);
+    if (O.kind == RSB_OPND_DUAL_BN_RELU) { U.a2 = __ldg(O.a + O.ku + k); U.d2 = __ldg(O.d + O.ku + k); }
 #pragma unroll
-        for (int e = 0; e < 4; e++) { g[e] = (r0 + e) / O.ns; sidx[e] = (int)(r0 + e - g[e] * O.ns); }
-    }
-    for (int cb = 0; cb < width; cb += 32) {
-        const int ct = cb + lane;            // channel inside the tile
-        if (ct >= width) break;              // tiles are multiples of 16 channels, not of 32
-        const int c = c_base + ct;           // logical channel of the operand
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (c < O.K) {
-            const int k = O.k0 + c;
-            const float a = O.a ? __ldg(O.a + k) : 0.f, d = O.d ? __ldg(O.d + k) : 0.f, b = O.b ? __ldg(O.b + k) : 0.f;
-            float a2 = 0.f, d2 = 0.f;
-            if (O.kind == RSB_OPND_DUAL_BN_RELU) { a2 = __ldg(O.a + O.ku + k); d2 = __ldg(O.d + O.ku + k); }
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-                if (r0 + e < rows) v[e] = opnd_eval1(O, r0 + e, k, a, b, d, a2, d2, g[e], sidx[e]);
+    for (int e = 0; e < 4; e++) {
+        const long r = r0 + e;
+        if (r >= rows) continue;
+        switch (O.kind) {
+        case RSB_OPND_RAW:
+        case RSB_OPND_BN_RELU:
+            U.u[e] = __ldg(O.U + (size_t)r * O.ldu + k);
+            break;
+        case RSB_OPND_DUAL_BN_RELU:
+            U.u[e] = __ldg(O.U + (size_t)r * O.ldu + k);
+            U.w[e] = __ldg(O.U + (size_t)r * O.ldu + O.ku + k);
+            break;
+        case RSB_OPND_AFFINE2:
+            U.u[e] = __ldg(O.U + (size_t)r * O.ldu + (k % O.ku));
+            U.w[e] = __ldg(O.V + (size_t)r * O.ldv + k);
+            break;
+        default: {
+            const long g = r / O.ns;
+            const int sidx = (int)(r - g * O.ns);
+            U.w[e] = __ldg(O.V + (size_t)r * O.ldv + k);
+            U.u[e] = __int_as_float(__ldg(O.arg + (size_t)g * O.ldu + k) == sidx ? 1 : 0);
+            U.dz[e] = __ldg(O.U + (size_t)g * O.ldu + k);
+            break;
         }
-        float4 hi, lo;
-        split4(v, hi, lo);
-        const int off = (ct >> 3) * (KC / 4) * 32 + k4 * 32 + (ct & 7) * 4;   // floats
-        *reinterpret_cast<float4 *>(hi_base + off) = hi;
-        *reinterpret_cast<float4 *>(lo_base + off) = lo;
+        }
     }
+}
+
+__device__ __forceinline__ void wunit_store(const WUnit &U, const Opnd &O, long row0, long rows, float *hi_base, float *lo_base)
+{
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (U.live) {
+        const long r0 = row0 + U.k4 * 4;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (r0 + e >= rows) continue;
+            switch (O.kind) {
+            case RSB_OPND_RAW: v[e] = U.u[e]; break;
+            case RSB_OPND_BN_RELU: v[e] = fmaxf(fmaf(U.u[e], U.a, U.d), 0.f); break;
+            case RSB_OPND_DUAL_BN_RELU: v[e] = fmaxf(fmaf(U.u[e], U.a, U.d) + fmaf(U.w[e], U.a2, U.d2), 0.f); break;
+            case RSB_OPND_AFFINE2: v[e] = fmaf(U.a, U.u[e], fmaf(U.b, U.w[e], U.d)); break;
+            default: v[e] = fmaf(U.a, __float_as_int(U.u[e]) ? U.dz[e] : 0.f, fmaf(U.b, U.w[e], U.d)); break;
+            }
+        }
+    }
+    float4 hi, lo;
+    split4(v, hi, lo);
+    const int off = (U.ct >> 3) * (KC / 4) * 32 + U.k4 * 32 + (U.ct & 7) * 4;   // floats
+    *reinterpret_cast<float4 *>(hi_base + off) = hi;
+    *reinterpret_cast<float4 *>(lo_base + off) = lo;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_constant__ WgradParams P)
@@ -578,7 +776,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     const size_t a_bytes = A_TILE_BYTES;                  // one of hi / lo of the G^T tile (128 channels x 32 rows)
     const size_t b_bytes = (size_t)NT * KC * 4;           // one of hi / lo of the X^T tile (NT channels x 32 rows)
     const size_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int STAGES = P.stages;
     Barriers *B = reinterpret_cast<Barriers *>(smem + STAGES * stage_bytes);
+    // single-tile problems never restage a channel block that holds no valid channel: zero it once
+    const bool skip_empty = P.m_tiles == 1 && P.n_tiles == 1;
+    if (skip_empty)
+        for (size_t i = tid; i < STAGES * stage_bytes / 16; i += THREADS) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
     const uint32_t tmem_base = cta_prologue(B, tid, warp);
 
     const long n_chunks = (P.rows + KC - 1) / KC;
@@ -587,21 +791,49 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
 
     if (my_chunks > 0) {
         if (warp < PROD_WARPS) {
+            const int grp = warp >> 2, w4 = warp & 3;
             uint32_t it = 0;
             for (int mt = 0; mt < P.m_tiles; mt++)
                 for (int nt = 0; nt < P.n_tiles; nt++)
                     for (long ci = 0; ci < my_chunks; ci++, it++) {
+                        if ((it & 1) != (uint32_t)grp) continue;
                         const int s = it % STAGES;
                         mbar_wait(&B->empty[s], ((it / STAGES) & 1) ^ 1);
                         unsigned char *st = smem + (size_t)s * stage_bytes;
                         const long row0 = (blockIdx.x + ci * gridDim.x) * (long)KC;
-                        wgrad_stage_operand(P.G, TM, mt * TM, row0, P.rows, reinterpret_cast<float *>(st),
-                                            reinterpret_cast<float *>(st + a_bytes), warp, lane);
-                        wgrad_stage_operand(P.X, NT, nt * NT, row0, P.rows, reinterpret_cast<float *>(st + 2 * a_bytes),
-                                            reinterpret_cast<float *>(st + 2 * a_bytes + b_bytes), warp, lane);
+                        // units of this warp for this chunk: 2 row quads x (channel blocks of G + channel blocks of X)
+                        const int vg = min(TM, P.M - mt * TM), vx = min(NT, P.N - nt * NT);
+                        const int nbg = skip_empty ? (vg + 31) / 32 : (TM + 31) / 32;
+                        const int nbx = skip_empty ? (vx + 31) / 32 : (NT + 31) / 32;
+                        const int per_h = nbg + nbx, n_units = 2 * per_h;
+                        float *g_hi = reinterpret_cast<float *>(st), *g_lo = reinterpret_cast<float *>(st + a_bytes);
+                        float *x_hi = reinterpret_cast<float *>(st + 2 * a_bytes), *x_lo = reinterpret_cast<float *>(st + 2 * a_bytes + b_bytes);
+                        constexpr int UB = 4;
+                        for (int u0 = 0; u0 < n_units; u0 += UB) {
+                            WUnit U[UB];
+#pragma unroll
+                            for (int i = 0; i < UB; i++) {
+                                const int u = u0 + i;
+                                U[i].which = -1;
+                                if (u < n_units) {
+                                    const int h = u / per_h, rem = u - h * per_h;
+                                    const bool isg = rem < nbg;
+                                    const int cb = (isg ? rem : rem - nbg) * 32;
+                                    if (cb + lane < (isg ? TM : NT)) {   // tiles are multiples of 16 channels, not of 32
+                                        U[i].which = isg ? 0 : 1;
+                                        wunit_load(U[i], isg ? P.G : P.X, isg ? mt * TM : nt * NT, cb, w4 + 4 * h, row0, P.rows, lane);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < UB; i++) {
+                                if (U[i].which == 0) wunit_store(U[i], P.G, row0, P.rows, g_hi, g_lo);
+                                else if (U[i].which == 1) wunit_store(U[i], P.X, row0, P.rows, x_hi, x_lo);
+                            }
+                        }
                         fence_proxy_async();
                         mbar_arrive(&B->full[s]);
-                        if (tid == 0) mbar_arrive(&B->full[s]);   // barrier counts PROD_THREADS + 1 (shared with gemm_rows)
+                        if ((tid & (GROUP_THREADS - 1)) == 0) mbar_arrive(&B->full[s]);   // barrier counts GROUP_THREADS + 1
                     }
         } else if (warp == MMA_WARP) {
             const uint32_t idesc = umma_idesc_tf32(TM, NT, false);
@@ -734,7 +966,23 @@ RSB_EXPORT int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float 
     P.NT = pick_nt(N);
     P.n_tiles = (N + P.NT - 1) / P.NT;
     P.k_chunks = (A->K + KC - 1) / KC;
-    const size_t smem = STAGES * (2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4) + sizeof(Barriers) + 4 * 32 * 33 * 4;
+    const size_t stage_b = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4;
+    const size_t fixed_b = sizeof(Barriers) + 4 * 32 * 33 * 4 + 1024;
+    const size_t budget = 227 * 1024 - fixed_b;
+    // asynchronous operand prefetch needs 16-byte aligned pieces
+    const bool al_u = (A->ldu % 4 == 0) && ((uintptr_t)A->U % 16 == 0) && (A->k0 % 4 == 0) &&
+                      (A->kind != RSB_OPND_DUAL_BN_RELU || A->ku % 4 == 0) && (A->kind != RSB_OPND_AFFINE2 || A->ku % 4 == 0);
+    const bool al_v = !A->V || ((A->ldv % 4 == 0) && ((uintptr_t)A->V % 16 == 0));
+    const size_t ring_b = 2 * 4 * (size_t)PROD_THREADS * 16;      // one ring slot: 2 pieces x 4 rows x 256 threads x 16 B
+    P.raw_depth = 0;
+    P.stages = (int)(budget / stage_b);
+    if (al_u && al_v && !getenv("RSB_TC_SYNC")) {
+        for (int rd = 3; rd >= 2 && P.raw_depth == 0; rd--)
+            if (budget >= 2 * stage_b + rd * ring_b) { P.raw_depth = rd; P.stages = (int)((budget - rd * ring_b) / stage_b); }
+    }
+    if (P.stages > STAGES_MAX) P.stages = STAGES_MAX;
+    RSB_REQUIRE(P.stages >= 2, "tile does not fit");
+    const size_t smem = P.stages * stage_b + fixed_b + P.raw_depth * ring_b;
     static bool attr_set = false;
     if (!attr_set) {
         RSB_CUDA(cudaFuncSetAttribute(gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -760,7 +1008,11 @@ RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *
     P.NT = pick_nt(P.N);
     P.m_tiles = (P.M + TM - 1) / TM;
     P.n_tiles = (P.N + P.NT - 1) / P.NT;
-    const size_t smem = STAGES * (2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4) + sizeof(Barriers);
+    const size_t stage_b = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4;
+    P.stages = (int)((227 * 1024 - sizeof(Barriers) - 1024) / stage_b);
+    if (P.stages > STAGES_MAX) P.stages = STAGES_MAX;
+    RSB_REQUIRE(P.stages >= 2, "tile does not fit");
+    const size_t smem = P.stages * stage_b + sizeof(Barriers) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         RSB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
