@@ -104,6 +104,16 @@ int rsb_furthestsampling_packed(int b, int n_max, const int *n_max_dev, const fl
 int rsb_knnquery_packed(int b, int m, int nsample, const float *xyz, const float *new_xyz, const int *offset,
                         const int *new_offset, int *idx, float *dist, int sqrt_out, cudaStream_t stream);
 
+/* Same results as rsb_knnquery_packed / rsb_knnquery_dense / rsb_knnquery_heap_dense (index-exact, same tie
+ * semantics), computed through a uniform grid built per call (counting sort, ~8 points per cell) instead of the
+ * reference's all-pairs scan.  packed != 0: segmentation layout (n_total/m_total rows, offset/new_offset, global ids);
+ * packed == 0: dense [b,n,3]/[b,m,3], local ids.  heap != 0: heap-order tie semantics.  workspace: caller-allocated
+ * device scratch of rsb_knn_grid_workspace_bytes(n_total, b) bytes. */
+long rsb_knn_grid_workspace_bytes(int n_total, int b);
+int rsb_knnquery_grid(int packed, int heap, int b, int n, int m, int n_total, int m_total, int nsample,
+                      const float *xyz, const float *new_xyz, const int *offset, const int *new_offset, int *idx,
+                      float *dist, int sqrt_out, void *workspace, long workspace_bytes, cudaStream_t stream);
+
 /* replaces grouping_forward/backward_cuda_launcher(m,nsample,c,...)                    seg/po/src/grouping/grouping_cuda_kernel.h:11-12
  * input [n,c], idx [m,nsample] -> output [m,nsample,c]. */
 int rsb_grouping_packed_forward(int m, int nsample, int c, const float *input, const int *idx, float *output,

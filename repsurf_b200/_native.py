@@ -34,6 +34,7 @@ _SIGS = {
     "rsb_interpolation_backward": [_i, _i, _i, _i, _p, _p, _p, _p],
     "rsb_furthestsampling_packed": [_i, _i, _p, _p, _p, _p, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],
+    "rsb_knnquery_grid": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _l],
     "rsb_grouping_packed_forward": [_i, _i, _i, _p, _p, _p],
     "rsb_grouping_packed_backward": [_i, _i, _i, _p, _p, _p],
     "rsb_interpolation_packed_forward": [_i, _i, _i, _p, _p, _p, _p],
@@ -49,7 +50,7 @@ _SIGS = {
     "rsb_bn_relu_backward": [_l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
-                                "rsb_linear_tc_weight_floats"])
+                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes"])
 
 
 def build(force=False):
@@ -78,6 +79,8 @@ def lib():
         L.rsb_abi_version.restype = _i
         L.rsb_linear_tc_weight_floats.restype = _l
         L.rsb_linear_tc_weight_floats.argtypes = [_i, _i]
+        L.rsb_knn_grid_workspace_bytes.restype = _l
+        L.rsb_knn_grid_workspace_bytes.argtypes = [_i, _i]
         _lib = L
     return _lib
 

@@ -16,6 +16,9 @@ from torch.autograd import Function
 
 from .. import _native as N
 
+# kNN: clouds with at least this many points (on average) go through the grid search; None = always all-pairs
+KNN_GRID_MIN_POINTS = 2048
+
 # sectorized FPS: keep the sector sizes on the device (no host sync, larger launch) or read back their maximum
 SECTOR_SIZES_ON_DEVICE = False
 
@@ -155,9 +158,18 @@ class KNNQuery(Function):
             new_xyz = xyz
         assert xyz.is_contiguous() and new_xyz.is_contiguous()
         m = new_xyz.shape[0]
+        n = xyz.shape[0]
+        b = offset.shape[0]
         idx = torch.empty(m, nsample, dtype=torch.int32, device=xyz.device)
         dist = torch.empty(m, nsample, dtype=torch.float32, device=xyz.device)
-        N.call("rsb_knnquery_packed", offset.shape[0], m, int(nsample), xyz, new_xyz, offset, new_offset, idx, dist, 1)
+        if KNN_GRID_MIN_POINTS is not None and n >= KNN_GRID_MIN_POINTS * b:
+            # same indices / distances as the all-pairs kernel, through a uniform grid (csrc/knn_grid.cu)
+            nbytes = int(N.lib().rsb_knn_grid_workspace_bytes(n, b))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+            N.call("rsb_knnquery_grid", 1, 1, b, 0, 0, n, m, int(nsample), xyz, new_xyz, offset, new_offset, idx, dist, 1,
+                   ws, nbytes)
+        else:
+            N.call("rsb_knnquery_packed", b, m, int(nsample), xyz, new_xyz, offset, new_offset, idx, dist, 1)
         ctx.mark_non_differentiable(idx, dist)
         return idx, dist
 

@@ -289,3 +289,45 @@ def test_full_size_properties_s3dis_shape():
     sl = slice(N, N + 256)
     D = torch.cdist(xyz[sl].double(), xyz[N:2 * N].double())
     assert torch.equal(D.topk(9, largest=False)[1] + N, nidx[sl].long())
+
+
+# ------------------------------------------------------------------------------------------- grid kNN == all-pairs kNN
+@pytest.mark.parametrize("sizes,k", [((5000, 3000), 9), ((40960,), 32), ((3000, 9000, 2500), 3), ((2500, 2100), 64)])
+def test_knn_grid_equals_allpairs(sizes, k, monkeypatch):
+    P = _seg()
+    xyz, off = _packed(sizes, 17)
+    q = xyz[::3].contiguous()
+    msizes = [len(range(a, b, 3)) for a, b in zip([0] + list(np.cumsum(sizes)[:-1]), np.cumsum(sizes))]
+    # rows of q must stay grouped per cloud: rebuild per cloud
+    parts, start = [], 0
+    for sz in sizes:
+        parts.append(xyz[start:start + sz][::3])
+        start += sz
+    q = torch.cat(parts).contiguous()
+    noff = torch.tensor(np.cumsum([p.shape[0] for p in parts]), dtype=torch.int32)
+    monkeypatch.setattr(P, "KNN_GRID_MIN_POINTS", None)
+    bi, bd = P.knnquery(k, xyz.to(cuda), q.to(cuda), off.to(cuda), noff.to(cuda))
+    monkeypatch.setattr(P, "KNN_GRID_MIN_POINTS", 1)
+    gi, gd = P.knnquery(k, xyz.to(cuda), q.to(cuda), off.to(cuda), noff.to(cuda))
+    assert torch.equal(bi, gi) and torch.equal(bd, gd)
+
+
+def test_knn_grid_lattice_and_degenerate_inputs(monkeypatch):
+    P = _seg()
+    monkeypatch.setattr(P, "KNN_GRID_MIN_POINTS", 1)
+    g = torch.Generator().manual_seed(8)
+    lat = torch.randint(-6, 7, (3000, 3), generator=g).float() * 0.5          # many exact ties -> replay path
+    off = torch.tensor([1200, 3000], dtype=torch.int32)
+    widx, wdist = O.knn_packed(9, lat, lat, off, off)
+    gidx, gdist = P.knnquery(9, lat.to(cuda), lat.to(cuda), off.to(cuda), off.to(cuda))
+    assert torch.equal(gidx.cpu(), widx) and _ulp_equal(gdist, wdist)
+    flat = torch.rand(2000, 3, generator=g) * torch.tensor([5.0, 5.0, 0.0])   # planar cloud (zero extent in z)
+    off1 = torch.tensor([2000], dtype=torch.int32)
+    widx, _ = O.knn_packed(16, flat, flat, off1, off1)
+    gidx, _ = P.knnquery(16, flat.to(cuda), flat.to(cuda), off1.to(cuda), off1.to(cuda))
+    assert torch.equal(gidx.cpu(), widx)
+    few = torch.rand(5, 3, generator=g)                                        # fewer points than k
+    off2 = torch.tensor([5], dtype=torch.int32)
+    widx, _ = O.knn_packed(9, few, few, off2, off2)
+    gidx, _ = P.knnquery(9, few.to(cuda), few.to(cuda), off2.to(cuda), off2.to(cuda))
+    assert torch.equal(gidx.cpu(), widx)
