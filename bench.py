@@ -58,39 +58,76 @@ def make_inputs(workload, clouds, n, seed, pin):
 
 # -------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  Uses NVML in-process
+    (nvidia_ml_py) from a background thread: an external `nvidia-smi -lms` loop measurably slows the step."""
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.stop_flag, self.thread, self.ok = gpu_index, [], False, None, False
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; map through the PCI bus id
+            bus = torch.cuda.get_device_properties(self.idx).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.idx), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                        h = hi
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nv, self.h, self.ok = pynvml, h, True
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.ok = False
+            return
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        def loop():
+            nv = self.nv
+            while not self.stop_flag:
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((float(sm), int(rs)))
+                except Exception:
+                    pass
+                time.sleep(0.4)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({k for _sm, rs in self.rows for k, bit in names.items() if rs & bit})
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm)}
 
 
 # -------------------------------------------------------------------------------------------- per-entry timing
+class _OpndInfo:
+    def __init__(self, o):
+        self.K, self.ku, self.kind = int(o.K), int(o.ku), int(o.kind)
+
+
+def _lite(x):
+    if isinstance(x, (int, float)) or x is None:
+        return x
+    if hasattr(x, "kind") and hasattr(x, "ku"):
+        return _OpndInfo(x)
+    return None
+
+
 class EntryTimer:
     """CUDA-event timing of every C-ABI call made through repsurf_b200._native.call (torch's current stream)."""
 
@@ -105,7 +142,8 @@ class EntryTimer:
             a.record()
             self.orig(name, *args)
             b.record()
-            self.ev.append((name, args[:5], a, b))
+            # keep only plain numbers: holding tensors / descriptors here would pin every activation of the step
+            self.ev.append((name, tuple(_lite(x) for x in args[:8]), a, b))
         self.native.call = timed
         return self
 
@@ -224,18 +262,12 @@ def main():
 
     model = (RepSurfSeg() if args.workload == "seg" else RepSurfCls()).to(dev).train()
     crit = nn.CrossEntropyLoss() if args.workload == "seg" else SmoothClsLoss()
+    from repsurf_b200.dist import FlatGrads, broadcast_module
     params = [p for p in model.parameters()]
+    broadcast_module(model)
     # one flat gradient buffer: backward accumulates straight into it, ONE all-reduce per step (3.9 MB seg / 5.9 MB cls)
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-    o = 0
-    for p in params:
-        p.grad = flat[o:o + p.numel()].view_as(p)
-        o += p.numel()
-    if world > 1:
-        for p in params:
-            dist.broadcast(p.data, 0)
-        for b in model.buffers():
-            dist.broadcast(b, 0)
+    fg = FlatGrads(params)
+    flat = fg.flat
     opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4)
 
     host = make_inputs(args.workload, wl["clouds"], wl["n"], 100 + rank, pin=True)
@@ -251,9 +283,7 @@ def main():
         else:
             loss = crit(model(inp[0]), inp[1])
         loss.backward()
-        if world > 1:
-            dist.all_reduce(flat)
-            flat.div_(world)
+        fg.allreduce_mean()
         opt.step()
         return loss
 
@@ -292,7 +322,8 @@ def main():
         clocks.start()
     _native.reset_launch_count()
     timed_entries = None if os.environ.get("RSB_TIME_ALL_ENTRIES") else {
-        "rsb_furthestsampling_packed", "rsb_furthestsampling_dense", "rsb_knnquery_packed", "rsb_knnquery_dense"}
+        "rsb_furthestsampling_packed", "rsb_furthestsampling_dense", "rsb_knnquery_packed", "rsb_knnquery_dense",
+        "rsb_knnquery_grid", "rsb_gemm_wgrad", "rsb_gemm_rows", "rsb_ballquery"}
     with EntryTimer(_native, timed_entries) as et:
         ms_step = timed(step_resident, args.steps)
     launches = _native.launch_count()
@@ -311,31 +342,72 @@ def main():
     value = clouds_total / (ms_step * 1e-3)
     e2e_value = clouds_total / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant repsurf_b200 kernel (by time inside the timed region) ----
-    hbm_peak, _tf_peak, peak_src = peaks()
-    dom = max(per_entry.items(), key=lambda kv: kv[1]["ms"]) if per_entry else None
-    roof = None
+    # ---- rooflines: every timed C-ABI entry against its own bound; "roofline" = the entry with the most time ----
+    hbm_peak, tf_peak, peak_src = peaks()
     entry_share = {k: round(v["ms"] / (ms_step * args.steps), 4) for k, v in per_entry.items()}
-    fps_names = ("rsb_furthestsampling_packed", "rsb_furthestsampling_dense")
-    fps = [(k, v) for k, v in per_entry.items() if k in fps_names]
-    if fps:
-        # FPS is the HBM-roofline kernel named by BASELINE.json; report its LARGEST launch shape
-        # (seg: sa1's launch; cls: sa1's 1024->512).  Algorithmic bytes from the streaming model.
-        if args.workload == "seg":
-            n, segs = wl["n"], wl["clouds"]
-            # training mode: sa1 is sectorized: 4 sectors/cloud of ~n/4 points -> n/16 samples each
-            alg = segs * 4 * fps_algorithmic_bytes(n / 4, n / 16)
-            note = f"sa1 sectorized FPS launch: {segs*4} segments of ~{n//4} pts -> {n//16} samples"
-        else:
-            alg = wl["clouds"] * fps_algorithmic_bytes(wl["n"], 512)
-            note = f"sa1 FPS launch: {wl['clouds']} clouds {wl['n']} -> 512"
-        k, v = fps[0]
+    dom = max(per_entry.items(), key=lambda kv: kv[1]["ms"]) if per_entry else None
+
+    def biggest(v):
         big = max(t for _a, t in v["each"])
-        big_avg = float(np.mean([t for _a, t in v["each"] if t > 0.5 * big]))
-        ach = alg / (big_avg * 1e-3) / 1e9
-        roof = {"kernel": "fps_kernel (" + k + ")", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src, "launch_ms": big_avg, "launch": note,
-                "algorithmic_bytes_per_launch": alg}
+        sel = [(a, t) for a, t in v["each"] if t > 0.6 * big]
+        return sel[0][0], float(np.mean([t for _a, t in sel]))
+
+    def opnd_bytes(o, rows):
+        per_row = {0: o.K, 1: o.K, 2: 2 * o.K, 3: o.K + min(o.K, o.ku), 4: o.K}[o.kind]
+        return rows * per_row * 4
+
+    rooflines = {}
+    for name, v in per_entry.items():
+        a, t_ms = biggest(v)
+        if name.startswith("rsb_furthestsampling"):
+            if name.endswith("packed"):
+                nseg, n_max = a[0], a[1]
+                m_seg = (wl["n"] // 4 // 4) if (args.workload == "seg" and nseg == wl["clouds"] * 4) else n_max // 4
+                alg = nseg * fps_algorithmic_bytes(n_max if nseg != wl["clouds"] * 4 else wl["n"] / 4, m_seg)
+                note = f"{nseg} segments, largest {n_max} points, ~{m_seg} samples each (streaming model, SURVEY 8d)"
+            else:
+                alg = a[0] * fps_algorithmic_bytes(a[1], a[2])
+                note = f"{a[0]} clouds {a[1]} -> {a[2]} (streaming model, SURVEY 8d)"
+            ach = alg / (t_ms * 1e-3) / 1e9
+            rooflines[name] = {"kernel": "fps_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": ach / hbm_peak, "launch_ms": t_ms, "launch": note, "algorithmic_bytes_per_launch": alg}
+        elif name == "rsb_gemm_wgrad":
+            rows_, G_, X_ = a[0], a[1], a[2]
+            alg = opnd_bytes(G_, rows_) + opnd_bytes(X_, rows_) + G_.K * X_.K * 4
+            flops = 2.0 * rows_ * G_.K * X_.K
+            ach = alg / (t_ms * 1e-3) / 1e9
+            rooflines[name] = {"kernel": "gemm_wgrad_kernel (tcgen05 3xTF32)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                               "unit": "GB/s", "frac": ach / hbm_peak, "launch_ms": t_ms,
+                               "launch": f"rows={rows_} dW[{G_.K}x{X_.K}], operand kinds {G_.kind}/{X_.kind}",
+                               "algorithmic_bytes_per_launch": alg, "algorithmic_tflops": flops / (t_ms * 1e-3) / 1e12}
+        elif name == "rsb_gemm_rows":
+            rows_, N_, A_ = a[0], a[1], a[2]
+            alg = opnd_bytes(A_, rows_) + rows_ * N_ * 4
+            ach = alg / (t_ms * 1e-3) / 1e9
+            rooflines[name] = {"kernel": "gemm_rows_kernel (tcgen05 3xTF32)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                               "unit": "GB/s", "frac": ach / hbm_peak, "launch_ms": t_ms,
+                               "launch": f"rows={rows_} K={A_.K} N={N_}, operand kind {A_.kind}",
+                               "algorithmic_bytes_per_launch": alg,
+                               "algorithmic_tflops": 2.0 * rows_ * N_ * A_.K / (t_ms * 1e-3) / 1e12}
+        elif name.startswith("rsb_knnquery"):
+            pairs = None
+            if name == "rsb_knnquery_grid":
+                n_tot, m_tot, b_ = a[5], a[6], a[2]
+                pairs = m_tot * (n_tot / max(b_, 1))
+                note = f"m={m_tot} queries x n={n_tot // max(b_, 1)} candidates/cloud, k={v['each'][0][0][7] if len(v['each'][0][0]) > 7 else '?'} (uniform-grid search)"
+            elif name == "rsb_knnquery_packed":
+                note = "all-pairs kernel (small clouds)"
+            if pairs:
+                fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # B200: 148 SMs x 128 FFMA lanes x 2 x 1.965 GHz
+                ach = pairs * 9 / (t_ms * 1e-3) / 1e12
+                rooflines[name] = {"kernel": "knn_grid_kernel", "bound": "fp32 (all-pairs model: 9 flop/pair)", "achieved": ach,
+                                   "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "launch_ms": t_ms, "launch": note,
+                                   "algorithmic_pairs_per_launch": pairs}
+    roof = None
+    if dom and dom[0] in rooflines:
+        roof = dict(rooflines[dom[0]])
+        roof["traffic"] = None
+        roof["peak_source"] = peak_src
 
     out = {
         "metric": metric, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -345,7 +417,7 @@ def main():
                    "optimizer_step": "SGD momentum inside the timed region", "tf32": False,
                    "l2": "per-step working set (activations > 126 MB) exceeds L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "roofline": roof, "entry_time_share": entry_share,
+        "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines, "entry_time_share": entry_share,
         "dominant_entry": dom[0] if dom else None, "clocks": clk,
     }
     if not args.no_cpu_baseline:
