@@ -199,6 +199,13 @@ int rsb_pool_forward(long G, int ns, int C, const float *Y, int ldy, const float
 int rsb_pool_backward_stats(long G, int ns, int C, const float *dOut, const int *arg, const float *Y, int ldy,
                             const float *sc, const float *sh, const float *mu, const float *inv, float *dm,
                             double *stats, cudaStream_t stream);
+/* rsb_pool_bn_backward_dense: in place Y := a*(arg==sample ? dm : 0) + b*Y + d  (max-pool + BatchNorm backward of the
+ *   last shared-MLP layer; Y, the stored pre-BN output, becomes dL/dY). */
+int rsb_pool_bn_backward_dense(long G, int ns, int C, const float *dm, const int *arg, float *Y, int ldy, const float *a,
+                               const float *b, const float *d, cudaStream_t stream);
+/* rsb_bn_apply: out = [relu](sc*Y + sh) (materialised BatchNorm(+ReLU) output). */
+int rsb_bn_apply(long rows, int C, const float *Y, int ldy, const float *sc, const float *sh, int relu, float *out,
+                 int ldo, cudaStream_t stream);
 /* rsb_bn_relu_backward: in place dA := dA where (sc*Y+sh [+ second half when dual]) > 0 else 0  (ReLU backward of
  *   a layer whose pre-BatchNorm output Y was stored), and stats[2C | 3C] += (sum dZ, sum dZ*xhat_1 [, sum dZ*xhat_2]). */
 int rsb_bn_relu_backward(long rows, int C, float *dA, int ldd, const float *Y, int ldy, const float *sc,

@@ -48,6 +48,8 @@ _SIGS = {
     "rsb_pool_backward_stats": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "rsb_bn_backward_coef": [_i, _l, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "rsb_bn_relu_backward": [_l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p],
+    "rsb_bn_apply": [_l, _i, _p, _i, _p, _p, _i, _p, _i],
+    "rsb_pool_bn_backward_dense": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
                                 "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes"])

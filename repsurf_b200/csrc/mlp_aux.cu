@@ -164,7 +164,81 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_kernel(long rows, int C, floa
     }
 }
 
+// out = [relu](sc*Y + sh): materialises a BatchNorm(+ReLU) output where a consumer outside the fused chain needs it
+__global__ void __launch_bounds__(256) bn_apply_kernel(long rows, int C, const float *__restrict__ Y, int ldy,
+                                                       const float *__restrict__ sc, const float *__restrict__ sh,
+                                                       int relu, float *__restrict__ out, int ldo)
+{
+    const int quads = C / 4;
+    const long total = rows * quads;
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const long r = i / quads;
+        const int c = (int)(i - r * quads) * 4;
+        const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + (size_t)r * ldy + c));
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(sc + c)), b = __ldg(reinterpret_cast<const float4 *>(sh + c));
+        float4 o = make_float4(fmaf(y.x, a.x, b.x), fmaf(y.y, a.y, b.y), fmaf(y.z, a.z, b.z), fmaf(y.w, a.w, b.w));
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4 *>(out + (size_t)r * ldo + c) = o;
+    }
+}
+
+// Max-pool backward + BatchNorm backward of the LAST shared-MLP layer, densified in place:
+//   Y[r,c] := a[c] * (arg[g,c] == r - g*ns ? dm[g,c] : 0) + b[c] * Y[r,c] + d[c]      (g = r / ns)
+// i.e. Y (stored pre-BN output, no longer needed) becomes dL/dY.  One streaming pass; the tensor-core wgrad and
+// dgrad then read a plain matrix instead of re-evaluating the selection per element.
+__global__ void __launch_bounds__(256) pool_bn_bwd_dense_kernel(long G, int ns, int C, const float *__restrict__ dm,
+                                                                const int *__restrict__ arg, float *__restrict__ Y, int ldy,
+                                                                const float *__restrict__ a, const float *__restrict__ b,
+                                                                const float *__restrict__ d)
+{
+    const int quads = C / 4;
+    const long total = G * quads;
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const long g = i / quads;
+        const int c = (int)(i - g * quads) * 4;
+        const float4 a4 = __ldg(reinterpret_cast<const float4 *>(a + c)), b4 = __ldg(reinterpret_cast<const float4 *>(b + c));
+        const float4 d4 = __ldg(reinterpret_cast<const float4 *>(d + c));
+        const float4 m4 = __ldg(reinterpret_cast<const float4 *>(dm + g * C + c));
+        const int4 s4 = __ldg(reinterpret_cast<const int4 *>(arg + g * C + c));
+        float *y = Y + (size_t)g * ns * ldy + c;
+        for (int s = 0; s < ns; s++) {
+            float4 v = *reinterpret_cast<float4 *>(y + (size_t)s * ldy);
+            v.x = fmaf(a4.x, s4.x == s ? m4.x : 0.f, fmaf(b4.x, v.x, d4.x));
+            v.y = fmaf(a4.y, s4.y == s ? m4.y : 0.f, fmaf(b4.y, v.y, d4.y));
+            v.z = fmaf(a4.z, s4.z == s ? m4.z : 0.f, fmaf(b4.z, v.z, d4.z));
+            v.w = fmaf(a4.w, s4.w == s ? m4.w : 0.f, fmaf(b4.w, v.w, d4.w));
+            *reinterpret_cast<float4 *>(y + (size_t)s * ldy) = v;
+        }
+    }
+}
+
 }  // namespace
+
+RSB_EXPORT int rsb_pool_bn_backward_dense(long G, int ns, int C, const float *dm, const int *arg, float *Y, int ldy,
+                                          const float *a, const float *b, const float *d, cudaStream_t stream)
+{
+    RSB_REQUIRE(C >= 4 && C % 4 == 0 && ldy % 4 == 0, "channels / pitch must be multiples of 4");
+    if (G == 0) return 0;
+    long blocks = (G * (C / 4) + 255) / 256;
+    if (blocks > (long)rsb_sm_count() * 16) blocks = (long)rsb_sm_count() * 16;
+    pool_bn_bwd_dense_kernel<<<(int)blocks, 256, 0, stream>>>(G, ns, C, dm, arg, Y, ldy, a, b, d);
+    RSB_CHECK_LAUNCH("pool_bn_bwd_dense_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+RSB_EXPORT int rsb_bn_apply(long rows, int C, const float *Y, int ldy, const float *sc, const float *sh, int relu,
+                            float *out, int ldo, cudaStream_t stream)
+{
+    RSB_REQUIRE(C >= 4 && C % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0, "channels / pitches must be multiples of 4");
+    if (rows == 0) return 0;
+    long blocks = (rows * (C / 4) + 255) / 256;
+    if (blocks > (long)rsb_sm_count() * 16) blocks = (long)rsb_sm_count() * 16;
+    bn_apply_kernel<<<(int)blocks, 256, 0, stream>>>(rows, C, Y, ldy, sc, sh, relu, out, ldo);
+    RSB_CHECK_LAUNCH("bn_apply_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
 
 RSB_EXPORT int rsb_bn_relu_backward(long rows, int C, float *dA, int ldd, const float *Y, int ldy, const float *sc,
                                     const float *sh, const float *mu, const float *inv, int dual, double *stats,

@@ -83,11 +83,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps in hardware instead of spinning
             : "memory");
     } while (!done);
 }
@@ -711,36 +711,57 @@ __device__ __forceinline__ void wunit_load(WUnit &U, const Opnd &O, int c_base, 
     if (!U.live) return;
     const int k = O.k0 + c;
     const long r0 = row0 + k4 * 4;
+    const int nr = (int)min(4L, rows - r0);          // valid rows of this quad (may be <= 0)
     if (O.a) U.a = __ldg(O.a + k);
     if (O.d) U.d = __ldg(O.d + k);
     if (O.b) U.b = __ldg(O.b + k);
-    if (O.kind == RSB_OPND_DUAL_BN_RELU) { U.a2 = __ldg(O.a + O.ku + k); U.d2 = __ldg(O.d + O.ku + k); }
+    switch (O.kind) {
+    case RSB_OPND_RAW:
+    case RSB_OPND_BN_RELU: {
+        const float *pu = O.U + (size_t)r0 * O.ldu + k;
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const long r = r0 + e;
-        if (r >= rows) continue;
-        switch (O.kind) {
-        case RSB_OPND_RAW:
-        case RSB_OPND_BN_RELU:
-            U.u[e] = __ldg(O.U + (size_t)r * O.ldu + k);
-            break;
-        case RSB_OPND_DUAL_BN_RELU:
-            U.u[e] = __ldg(O.U + (size_t)r * O.ldu + k);
-            U.w[e] = __ldg(O.U + (size_t)r * O.ldu + O.ku + k);
-            break;
-        case RSB_OPND_AFFINE2:
-            U.u[e] = __ldg(O.U + (size_t)r * O.ldu + (k % O.ku));
-            U.w[e] = __ldg(O.V + (size_t)r * O.ldv + k);
-            break;
-        default: {
-            const long g = r / O.ns;
-            const int sidx = (int)(r - g * O.ns);
-            U.w[e] = __ldg(O.V + (size_t)r * O.ldv + k);
-            U.u[e] = __int_as_float(__ldg(O.arg + (size_t)g * O.ldu + k) == sidx ? 1 : 0);
-            U.dz[e] = __ldg(O.U + (size_t)g * O.ldu + k);
-            break;
+        for (int e = 0; e < 4; e++) if (e < nr) U.u[e] = __ldg(pu + (size_t)e * O.ldu);
+        break;
+    }
+    case RSB_OPND_DUAL_BN_RELU: {
+        U.a2 = __ldg(O.a + O.ku + k);
+        U.d2 = __ldg(O.d + O.ku + k);
+        const float *pu = O.U + (size_t)r0 * O.ldu + k;
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (e < nr) { U.u[e] = __ldg(pu + (size_t)e * O.ldu); U.w[e] = __ldg(pu + (size_t)e * O.ldu + O.ku); }
+        break;
+    }
+    case RSB_OPND_AFFINE2: {
+        const float *pu = O.U + (size_t)r0 * O.ldu + (k % O.ku);
+        const float *pv = O.V + (size_t)r0 * O.ldv + k;
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (e < nr) { U.u[e] = __ldg(pu + (size_t)e * O.ldu); U.w[e] = __ldg(pv + (size_t)e * O.ldv); }
+        break;
+    }
+    default: {
+        const float *pv = O.V + (size_t)r0 * O.ldv + k;
+        // rows of a quad share their pooling group whenever ns % 4 == 0 (r0 is a multiple of 4)
+        const bool same = (O.ns & 3) == 0;
+        const int g0 = (int)(r0 / O.ns), s0 = (int)(r0 - (long)g0 * O.ns);
+        int arg0 = 0;
+        float dz0 = 0.f;
+        if (same && nr > 0) { arg0 = __ldg(O.arg + (size_t)g0 * O.ldu + k); dz0 = __ldg(O.U + (size_t)g0 * O.ldu + k); }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (e >= nr) continue;
+            U.w[e] = __ldg(pv + (size_t)e * O.ldv);
+            if (same) {
+                U.u[e] = __int_as_float(arg0 == s0 + e ? 1 : 0);
+                U.dz[e] = dz0;
+            } else {
+                const long r = r0 + e;
+                const long g = r / O.ns;
+                U.u[e] = __int_as_float(__ldg(O.arg + (size_t)g * O.ldu + k) == (int)(r - g * O.ns) ? 1 : 0);
+                U.dz[e] = __ldg(O.U + (size_t)g * O.ldu + k);
+            }
         }
-        }
+        break;
+    }
     }
 }
 

@@ -85,6 +85,11 @@ class RepSurfSeg(nn.Module):
         f2 = self.fp3([l2[0], l2[2], l2[3]], [l3[0], f3, l3[3]])
         f1 = self.fp2([l1[0], l1[2], l1[3]], [l2[0], f2, l2[3]])
         f0 = self.fp1([l0[0], None, l0[3]], [l1[0], f1, l1[3]])
+        if f0.is_cuda and self.training:
+            # same head (Linear-BN-ReLU-Dropout-Linear), GEMMs + BatchNorm on the tensor cores
+            from . import tc
+            c = self.classifier
+            return tc.linear(c[3](tc.linear_bn(f0, c[0], c[1], relu=True)), c[4])
         return self.classifier(f0)
 
 

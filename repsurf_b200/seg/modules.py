@@ -115,13 +115,14 @@ class SurfaceFeaturePropagationCD(nn.Module):
         xyz2, points2, offset2 = pos_feat_off2
         idx, dist = P.knnquery(3, xyz2, xyz1, offset2, offset1)             # coarse neighbours of every fine point
         weight = P._idw(dist).contiguous()
-        coarse = self.norm_f0(self.mlp_f0(points2))                         # projected BEFORE interpolation (:267)
+        from .. import tc
+        coarse = tc.linear_bn(points2, self.mlp_f0, self.norm_f0, relu=False)   # projected BEFORE interpolation (:267)
         x = P._InterpApply.apply(coarse, idx, weight)
         if self.skip:
-            x = x + self.norm_s0(self.mlp_s0(points1))
+            x = x + tc.linear_bn(points1, self.mlp_s0, self.norm_s0, relu=False)
         x = F.relu(x)
         for lin, bn in zip(self.mlp_convs, self.mlp_bns):
-            x = F.relu(bn(lin(x)))
+            x = tc.linear_bn(x, lin, bn, relu=True)
         return x
 
 

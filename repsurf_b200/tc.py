@@ -174,7 +174,12 @@ class _FusedSAMLP(Function):
         co = torch.empty(5, CL, device=dev)
         N.call("rsb_bn_backward_coef", CL, R, st, 0, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
         grads[("g", L)], grads[("be", L)] = co[3], co[4]
-        Gop = opnd(OPND_POOLED, dm, CL, a=co[0], b=co[1], d=co[2], V=Ys[L], arg=arg, ns=ns) if L > 0 else None
+        if L > 0 and CL % 4 == 0:
+            # densify dL/dY_L in place of the stored Y_L (one streaming pass); the GEMMs then read a plain matrix
+            N.call("rsb_pool_bn_backward_dense", G, ns, CL, dm, arg, Ys[L], Ys[L].stride(0), co[0], co[1], co[2])
+            Gop = opnd(OPND_RAW, Ys[L], CL)
+        else:
+            Gop = opnd(OPND_POOLED, dm, CL, a=co[0], b=co[1], d=co[2], V=Ys[L], arg=arg, ns=ns) if L > 0 else None
         if L == 0:
             raise RuntimeError("shared MLP needs at least two layers")
         for l in range(L, 0, -1):
@@ -265,3 +270,111 @@ def sa_mlp_fused(rows, pos_channel, mod, nsample):
             var = (sti[C:] / R - mean * mean).clamp_min(0) * (R / max(R - 1, 1))
             _update_running(bn, mean.float(), var.float())
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# single layers on the tensor cores: Linear (+ train-mode BatchNorm (+ ReLU)) over rows, hand-written backward.
+# Used by SurfaceFeaturePropagationCD, the umbrella MLP and the segmentation head.
+# ------------------------------------------------------------------------------------------------------------
+class _LinearBN(Function):
+    @staticmethod
+    def forward(ctx, X, W, bias, gamma, beta, relu, eps):
+        dev = X.device
+        X = X.contiguous()
+        R, K = X.shape
+        Nn = W.shape[0]
+        W2 = W.reshape(Nn, -1).detach().contiguous()
+        Wp, _, _ = prep_weight(W2)
+        Y = torch.empty(R, Nn, device=dev)
+        st = torch.zeros(2 * Nn, dtype=torch.float64, device=dev)
+        gemm_rows(R, Nn, opnd(OPND_RAW, X, K), Wp, Y=Y, bias=None if bias is None else bias.detach(), stats=st)
+        sc, sh, mu, inv = _bn_finalize(Nn, R, st, gamma.detach(), beta.detach(), eps, 0.0, None, None, dev)
+        out = torch.empty(R, Nn, device=dev)
+        N.call("rsb_bn_apply", R, Nn, Y, Nn, sc, sh, 1 if relu else 0, out, Nn)
+        ctx.relu = relu
+        ctx.w_shape = tuple(W.shape)
+        ctx.has_bias = bias is not None
+        ctx.saved = (X, W2, Y, sc, sh, mu, inv)
+        ctx.mark_non_differentiable(st)
+        return out, st
+
+    @staticmethod
+    def backward(ctx, dOut, _st):
+        X, W2, Y, sc, sh, mu, inv = ctx.saved
+        dev = X.device
+        R, K = X.shape
+        Nn = W2.shape[0]
+        dZ = dOut.contiguous().clone()
+        st = torch.zeros(2 * Nn, dtype=torch.float64, device=dev)
+        if ctx.relu:
+            msc, msh = sc, sh
+        else:   # no activation: mask always on (z = 0*y + 1 > 0), statistics still needed
+            msc, msh = torch.zeros(Nn, device=dev), torch.ones(Nn, device=dev)
+        N.call("rsb_bn_relu_backward", R, Nn, dZ, Nn, Y, Nn, msc, msh, mu, inv, 0, st)
+        co = torch.empty(5, Nn, device=dev)
+        N.call("rsb_bn_backward_coef", Nn, R, st, 0, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
+        G = opnd(OPND_AFFINE2, dZ, Nn, a=co[0], b=co[1], d=co[2], V=Y, ku=Nn)
+        dW = torch.zeros(Nn, K, device=dev)
+        gemm_wgrad(R, G, opnd(OPND_RAW, X, K), dW)
+        dX = None
+        if ctx.needs_input_grad[0]:
+            WpT, _, _ = prep_weight(W2, transposed=True)
+            dX = torch.empty(R, K, device=dev)
+            gemm_rows(R, K, G, WpT, Y=dX)
+        db = torch.zeros(Nn, device=dev) if ctx.has_bias else None      # a bias in front of BatchNorm has zero gradient
+        return dX, dW.reshape(ctx.w_shape), db, co[3], co[4], None, None
+
+
+class _Linear(Function):
+    @staticmethod
+    def forward(ctx, X, W, bias):
+        X = X.contiguous()
+        R, K = X.shape
+        Nn = W.shape[0]
+        W2 = W.detach().contiguous()
+        Wp, _, _ = prep_weight(W2)
+        Y = torch.empty(R, Nn, device=X.device)
+        gemm_rows(R, Nn, opnd(OPND_RAW, X, K), Wp, Y=Y, bias=None if bias is None else bias.detach())
+        ctx.saved = (X, W2)
+        ctx.has_bias = bias is not None
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W2 = ctx.saved
+        R, K = X.shape
+        Nn = W2.shape[0]
+        dY = dY.contiguous()
+        dW = torch.zeros(Nn, K, device=X.device)
+        gemm_wgrad(R, opnd(OPND_RAW, dY, Nn), opnd(OPND_RAW, X, K), dW)
+        dX = None
+        if ctx.needs_input_grad[0]:
+            WpT, _, _ = prep_weight(W2, transposed=True)
+            dX = torch.empty(R, K, device=X.device)
+            gemm_rows(R, K, opnd(OPND_RAW, dY, Nn), WpT, Y=dX)
+        return dX, dW, (dY.sum(0) if ctx.has_bias else None)
+
+
+def linear_bn(x, lin, bn, relu):
+    """[relu](bn(lin(x))) over rows.  Training mode on CUDA runs on the tensor cores; eval falls back to torch."""
+    if not (bn.training and x.is_cuda and lin.weight.shape[0] % 4 == 0):
+        w = lin.weight
+        y = torch.nn.functional.linear(x, w.view(w.shape[0], -1), lin.bias)
+        y = torch.nn.functional.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
+                                           0.0 if bn.momentum is None else bn.momentum, bn.eps)
+        if bn.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return torch.relu(y) if relu else y
+    out, st = _LinearBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, relu, bn.eps)
+    R, C = x.shape[0], lin.weight.shape[0]
+    with torch.no_grad():
+        mean = st[:C] / R
+        var = (st[C:] / R - mean * mean).clamp_min(0) * (R / max(R - 1, 1))
+        _update_running(bn, mean.float(), var.float())
+    return out
+
+
+def linear(x, lin):
+    if not x.is_cuda:
+        return torch.nn.functional.linear(x, lin.weight, lin.bias)
+    return _Linear.apply(x, lin.weight, lin.bias)

@@ -102,3 +102,45 @@ def test_fused_sa_mlp_matches_fp64_torch(G, ns, pos_c, feat_c, mlp, conv):
             assert float(p.grad.abs().max()) == 0.0 and float(q.grad.abs().max()) < 1e-6 * max(1.0, float(go.abs().sum()))
         else:
             assert _rel(p.grad, q.grad) < 2e-4, n
+
+
+@pytest.mark.parametrize("R,K,Nn,relu", [(5000, 128, 128, True), (777, 512, 256, False), (3000, 64, 256, True), (100, 256, 128, False)])
+def test_linear_bn_layer_matches_fp64_torch(R, K, Nn, relu):
+    import copy
+    import torch.nn as nn
+    from repsurf_b200 import tc
+    torch.manual_seed(R)
+    lin, bn = nn.Linear(K, Nn).to(cuda), nn.BatchNorm1d(Nn).to(cuda).train()
+    nn.init.uniform_(bn.weight, 0.5, 1.5)
+    nn.init.normal_(bn.bias, 0, 0.2)
+    lin2, bn2 = copy.deepcopy(lin).double(), copy.deepcopy(bn).double()
+    x = torch.randn(R, K, device=cuda)
+    xa, xb = x.clone().requires_grad_(True), x.double().requires_grad_(True)
+    out = tc.linear_bn(xa, lin, bn, relu)
+    want = bn2(lin2(xb))
+    want = torch.relu(want) if relu else want
+    assert _rel(out, want) < 1e-5
+    go = torch.randn_like(out)
+    out.backward(go)
+    want.backward(go.double())
+    assert _rel(xa.grad, xb.grad) < 2e-4
+    assert _rel(lin.weight.grad, lin2.weight.grad) < 2e-4
+    assert _rel(bn.weight.grad, bn2.weight.grad) < 2e-4 and _rel(bn.bias.grad, bn2.bias.grad) < 2e-4
+    assert _rel(bn.running_mean.double(), bn2.running_mean) < 1e-5 and _rel(bn.running_var.double(), bn2.running_var) < 1e-5
+
+
+def test_plain_linear_matches_fp64_torch():
+    import copy
+    import torch.nn as nn
+    from repsurf_b200 import tc
+    torch.manual_seed(5)
+    lin = nn.Linear(128, 13).to(cuda)
+    lin2 = copy.deepcopy(lin).double()
+    x = torch.randn(4000, 128, device=cuda)
+    xa, xb = x.clone().requires_grad_(True), x.double().requires_grad_(True)
+    out, want = tc.linear(xa, lin), lin2(xb)
+    assert _rel(out, want) < 1e-5
+    go = torch.randn_like(out)
+    out.backward(go)
+    want.backward(go.double())
+    assert _rel(xa.grad, xb.grad) < 1e-5 and _rel(lin.weight.grad, lin2.weight.grad) < 1e-5 and _rel(lin.bias.grad, lin2.bias.grad) < 1e-5
