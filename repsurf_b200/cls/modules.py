@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from . import pointops as P
 from ..seg import pointops as PP
 from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, linear_rows, sa_mlp
+from ..mlp import bn_rows, linear_rows, pack_rows, sa_mlp
 
 
 def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_normal, return_polar):
@@ -36,16 +36,16 @@ def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_
     new_normal = P.gathering(normal.contiguous(), fps_idx)              # [B,Cn,m]
     idx = P.ballquery(radius, nsample, xyz, new_xyz)                    # [B,m,ns] local ids
     gidx = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N).view(B, 1, 1)).view(B * npoint, nsample)
+    R = B * npoint * nsample
     rel = PP.grouping(xyz.view(B * N, 3), gidx) - new_xyz.view(B * npoint, 1, 3)       # [B*m,ns,3]
-    parts = [rel]
-    if return_polar:
-        parts.append(xyz2sphere(rel))
+    pos = torch.cat([rel, xyz2sphere(rel)], dim=-1) if return_polar else rel
+    feats = []
     if feature is None or return_normal:
-        parts.append(PP.grouping(normal.transpose(1, 2).reshape(B * N, -1), gidx))
+        feats.append(PP.grouping(normal.transpose(1, 2).reshape(B * N, -1), gidx).view(R, -1))
     if feature is not None:
-        parts.append(PP.grouping(feature.transpose(1, 2).reshape(B * N, -1), gidx))
-    rows = torch.cat(parts, dim=-1)
-    return new_xyz.transpose(1, 2).contiguous(), new_normal, rows.view(B * npoint * nsample, -1)
+        feats.append(PP.grouping(feature.transpose(1, 2).reshape(B * N, -1), gidx).view(R, -1))
+    rows, p4, f = pack_rows(pos.reshape(R, -1), feats)
+    return new_xyz.transpose(1, 2).contiguous(), new_normal, rows, (p4, f)
 
 
 def _all_inputs(center_cf, normal, feature, return_normal, return_polar):
@@ -54,13 +54,10 @@ def _all_inputs(center_cf, normal, feature, return_normal, return_polar):
     B, _, N = center_cf.shape
     new_center = torch.zeros(B, 3, 1, device=center_cf.device, dtype=center_cf.dtype)
     xyz = center_cf.transpose(1, 2)
-    parts = [xyz]
-    if return_polar:
-        parts.append(xyz2sphere(xyz))
-    if return_normal:
-        parts.append(normal.transpose(1, 2))
-    parts.append(feature.transpose(1, 2))
-    return new_center, new_center, torch.cat(parts, dim=-1).reshape(B * N, -1)
+    pos = torch.cat([xyz, xyz2sphere(xyz)], dim=-1) if return_polar else xyz
+    feats = ([normal.transpose(1, 2).reshape(B * N, -1)] if return_normal else []) + [feature.transpose(1, 2).reshape(B * N, -1)]
+    rows, p4, f = pack_rows(pos.reshape(B * N, -1), feats)
+    return new_center, new_center, rows, (p4, f)
 
 
 class SurfaceAbstractionCD(nn.Module):
@@ -89,14 +86,14 @@ class SurfaceAbstractionCD(nn.Module):
     def forward(self, center, normal, feature):
         B, N = center.shape[0], center.shape[2]
         if self.group_all:
-            new_center, new_normal, rows = _all_inputs(center, normal, feature, self.return_normal, self.return_polar)
+            new_center, new_normal, rows, layout = _all_inputs(center, normal, feature, self.return_normal, self.return_polar)
             groups, ns = 1, N
         else:
-            new_center, new_normal, rows = _grouped_inputs(self.npoint, self.radius, self.nsample, center, normal,
-                                                           feature, self.return_normal, self.return_polar)
+            new_center, new_normal, rows, layout = _grouped_inputs(self.npoint, self.radius, self.nsample, center, normal,
+                                                                   feature, self.return_normal, self.return_polar)
             groups, ns = self.npoint, self.nsample
         # channel de-differentiation: position and feature channels get their own first layer (:236-239)
-        pooled = sa_mlp(rows, self.pos_channel, self, ns)                # [B*groups, C']
+        pooled = sa_mlp(rows, self.pos_channel, self, ns, layout)        # [B*groups, C']
         return new_center, new_normal, pooled.view(B, groups, -1).transpose(1, 2).contiguous()
 
 

@@ -27,14 +27,33 @@ def bn_rows(x, bn):
                         0.0 if bn.momentum is None else bn.momentum, bn.eps)
 
 
-def sa_mlp(rows, pos_channel, mod, nsample):
+def pack_rows(pos, feats):
+    """Row matrix of a grouped level with 16-byte aligned column blocks: [pos | 0-pad to 4 | feats... | 0-pad to 4].
+    pos [R, P]; feats: list of [R, c_i].  Returns (rows [R, P4 + F4], P4, F).  Aligned blocks let the tensor-core
+    kernels use 128-bit asynchronous loads / stores for the operand and for the feature gradient."""
+    R, P = pos.shape
+    F_ = sum(f.shape[1] for f in feats)
+    P4, F4 = (P + 3) // 4 * 4, (F_ + 3) // 4 * 4
+    parts = [pos]
+    if P4 > P:
+        parts.append(pos.new_zeros(R, P4 - P))
+    parts += feats
+    if F4 > F_:
+        parts.append(pos.new_zeros(R, F4 - F_))
+    return torch.cat(parts, dim=-1), P4, F_
+
+
+def sa_mlp(rows, pos_channel, mod, nsample, layout=None):
     """Shared MLP + max-pool of a SurfaceAbstractionCD level.  Training mode runs the fused tcgen05 path
     (repsurf_b200.tc: 3xTF32 GEMMs with BatchNorm/ReLU/pool folded into operand loads and epilogues, hand-written
     backward); eval mode (running statistics, no autograd through BatchNorm statistics) uses the row-matrix
     composition below."""
     if mod.training and rows.is_cuda and len(mod.mlp_convs) >= 1:
         from . import tc
-        return tc.sa_mlp_fused(rows, pos_channel, mod, nsample)
+        return tc.sa_mlp_fused(rows, pos_channel, mod, nsample, layout)
+    if layout is not None:   # strip the alignment padding for the plain composition
+        P4, F_ = layout
+        rows = torch.cat([rows[:, :pos_channel], rows[:, P4:P4 + F_]], dim=-1)
     return sa_mlp_rows(rows, pos_channel, mod, nsample)
 
 

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import pointops as P
 from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, linear_rows, sa_mlp
+from ..mlp import bn_rows, linear_rows, pack_rows, sa_mlp
 
 
 def strided_offsets(offset, stride):
@@ -35,7 +35,8 @@ def strided_offsets(offset, stride):
 
 def _sample_and_group(stride, nsample, center, normal, feature, offset, return_polar, num_sector, training):
     """ref: segmentation/modules/repsurface_utils.py:15-51.
-    -> new_center [M,3], new_normal [M,Cn], grouped [M,ns,C] (C = [rel xyz, polar?, normal, feature?]), new_offset."""
+    -> new_center [M,3], new_normal [M,Cn], rows [M*ns, C4] ([rel xyz, polar? | pad | normal, feature? | pad], see
+       mlp.pack_rows), (first feature column, feature channels), new_offset."""
     if stride > 1:
         new_offset = strided_offsets(offset, stride)
         if num_sector > 1 and training:
@@ -48,14 +49,14 @@ def _sample_and_group(stride, nsample, center, normal, feature, offset, return_p
     else:
         new_center, new_normal, new_offset = center, normal, offset
     group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
+    M = new_center.shape[0]
     rel = P.grouping(center, group_idx) - new_center.unsqueeze(1)
-    parts = [rel]
-    if return_polar:
-        parts.append(xyz2sphere(rel))
-    parts.append(P.grouping(normal.contiguous(), group_idx))
+    pos = torch.cat([rel, xyz2sphere(rel)], dim=-1) if return_polar else rel
+    feats = [P.grouping(normal.contiguous(), group_idx).view(M * nsample, -1)]
     if feature is not None:
-        parts.append(P.grouping(feature.contiguous(), group_idx))
-    return new_center, new_normal, torch.cat(parts, dim=-1), new_offset
+        feats.append(P.grouping(feature.contiguous(), group_idx).view(M * nsample, -1))
+    rows, p4, f = pack_rows(pos.reshape(M * nsample, -1), feats)
+    return new_center, new_normal, rows, (p4, f), new_offset
 
 
 class SurfaceAbstractionCD(nn.Module):
@@ -83,11 +84,10 @@ class SurfaceAbstractionCD(nn.Module):
 
     def forward(self, pos_nor_feat_off):
         center, normal, feature, offset = pos_nor_feat_off
-        new_center, new_normal, x, new_offset = _sample_and_group(
+        new_center, new_normal, rows, layout, new_offset = _sample_and_group(
             self.stride, self.nsample, center, normal, feature, offset, self.return_polar, self.num_sector,
             self.training)
-        M, ns, C = x.shape
-        return [new_center, new_normal, sa_mlp(x.view(M * ns, C), self.pos_channel, self, ns), new_offset]
+        return [new_center, new_normal, sa_mlp(rows, self.pos_channel, self, self.nsample, layout), new_offset]
 
 
 class SurfaceFeaturePropagationCD(nn.Module):

@@ -114,11 +114,11 @@ class _FusedSAMLP(Function):
         W_l, b_l, W_f, b_f, g_l, be_l, g_f, be_f = params[:8]
         C0 = W_l.shape[0]
         W_l2, W_f2 = W_l.reshape(C0, -1), W_f.reshape(C0, -1)
-        F = Cin - P
+        P4, F = meta["feat_col"], meta["feat_channels"]      # feature columns live at [P4, P4 + F)
         # block-diagonal first layer: one GEMM produces [y_l | y_f]
         Wbd = torch.zeros(2 * C0, Cin, device=dev)
         Wbd[:C0, :P] = W_l2
-        Wbd[C0:, P:] = W_f2
+        Wbd[C0:, P4:P4 + F] = W_f2
         bias0 = torch.cat([b_l, b_f]).detach()
         Wp0, _, _ = prep_weight(Wbd)
         Y0 = torch.empty(R, 2 * C0, device=dev)
@@ -216,18 +216,18 @@ class _FusedSAMLP(Function):
         dWbd = torch.zeros(2 * C0, Cin, device=dev)
         gemm_wgrad(R, Gop, opnd(OPND_RAW, X, Cin), dWbd)
         dX = None
+        P4, F = meta["feat_col"], meta["feat_channels"]
         if ctx.needs_input_grad[0]:
-            F = Cin - P
             dX = torch.zeros(R, Cin, device=dev)
-            Wf = Wbd[C0:, P:].contiguous()                   # [C0, F]
+            Wf = Wbd[C0:, P4:P4 + F].contiguous()            # [C0, F]
             WpT, _, _ = prep_weight(Wf, transposed=True)     # operand [N=F, K=C0]
             Gf = opnd(OPND_AFFINE2, dZ0, C0, a=cop0[0], b=cop0[1], d=cop0[2], V=Ys[0], ku=C0, k0=C0)
-            gemm_rows(R, F, Gf, WpT, Y=dX, ldy=Cin, y_off=P)
+            gemm_rows(R, F, Gf, WpT, Y=dX, ldy=Cin, y_off=P4)
         # ---- assemble parameter gradients in the order of *params
         W_l_shape, W_f_shape = meta["W_l_shape"], meta["W_f_shape"]
         zero = lambda n: torch.zeros(n, device=dev)
         out = [dX, None,
-               dWbd[:C0, :P].reshape(W_l_shape), zero(C0), dWbd[C0:, P:].reshape(W_f_shape), zero(C0),
+               dWbd[:C0, :P].reshape(W_l_shape), zero(C0), dWbd[C0:, P4:P4 + F].reshape(W_f_shape), zero(C0),
                grads[("g", 0)][:C0], grads[("be", 0)][:C0], grads[("g", 0)][C0:], grads[("be", 0)][C0:]]
         for i in range(n_extra):
             out += [grads[("W", i + 1)].reshape(meta["W_shapes"][i]), zero(grads[("W", i + 1)].shape[0]),
@@ -243,17 +243,20 @@ def _update_running(bn, mean, var_unbiased):
         bn.num_batches_tracked.add_(1)
 
 
-def sa_mlp_fused(rows, pos_channel, mod, nsample):
-    """Drop-in for mlp.sa_mlp_rows on the tensor cores (training mode).  rows [G*nsample, C] -> [G, mlp[-1]]."""
+def sa_mlp_fused(rows, pos_channel, mod, nsample, layout=None):
+    """Drop-in for mlp.sa_mlp_rows on the tensor cores (training mode).  rows [G*nsample, C] -> [G, mlp[-1]].
+    layout = (first feature column, feature channels) when the row matrix carries alignment padding (mlp.pack_rows)."""
     bns = [mod.bn_l0, mod.bn_f0] + list(mod.mlp_bns)
     params = [mod.mlp_l0.weight, mod.mlp_l0.bias, mod.mlp_f0.weight, mod.mlp_f0.bias,
               mod.bn_l0.weight, mod.bn_l0.bias, mod.bn_f0.weight, mod.bn_f0.bias]
     for lin, bn in zip(mod.mlp_convs, mod.mlp_bns):
         params += [lin.weight, lin.bias, bn.weight, bn.bias]
-    meta = dict(ns=nsample, pos_channel=pos_channel, eps=mod.bn_l0.eps, n_extra=len(mod.mlp_convs),
+    feat_col, feat_channels = layout if layout is not None else (pos_channel, rows.shape[1] - pos_channel)
+    meta = dict(ns=nsample, pos_channel=pos_channel, feat_col=feat_col, feat_channels=feat_channels,
+                eps=mod.bn_l0.eps, n_extra=len(mod.mlp_convs),
                 W_l_shape=tuple(mod.mlp_l0.weight.shape), W_f_shape=tuple(mod.mlp_f0.weight.shape),
                 W_shapes=[tuple(l.weight.shape) for l in mod.mlp_convs])
-    res = _FusedSAMLP.apply(rows.contiguous(), meta, *params)
+    res = _FusedSAMLP.apply(rows if rows.stride(1) == 1 else rows.contiguous(), meta, *params)
     out, stats = res[0], res[1:]
     # running statistics (same side effects as the BatchNorm modules): batch mean, UNBIASED batch variance
     R = rows.shape[0]
