@@ -387,78 +387,127 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
             // ===== producers, asynchronous path: every thread owns 4 rows x one channel quad of each chunk and
             // prefetches its own 16-byte pieces RD chunks ahead with cp.async into a private shared-memory ring
             // (no registers held, no cross-thread hand-off), so ~RD * 32 KB per SM are always in flight.
-            constexpr int RD_MAX = 3;
+            // Everything that does not change per chunk (shared-memory offsets, row pointers, validity) is hoisted:
+            // the per-chunk work is address adds, the transform itself and the hi/lo split.
             const int RD = P.raw_depth;
-            float4 *ring = reinterpret_cast<float4 *>(stat_tile + 4 * 32 * 33);       // [RD][2 pieces][4 rows][256 threads]
             const int k4 = tid & 7, rsub = tid >> 3;                                   // rows rsub + 32*j
+            constexpr uint32_t PIECE_STRIDE = PROD_THREADS * 16;                       // bytes between (piece, j) planes
+            constexpr uint32_t SLOT_BYTES = 2 * 4 * PIECE_STRIDE;
+            const uint32_t ring0 = rsb_smem_addr(stat_tile + 4 * 32 * 33) + (uint32_t)tid * 16;
+            uint32_t st_off[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int r = rsub + 32 * j;
+                st_off[j] = (uint32_t)(((r >> 3) * (KC / 4) * 32 + k4 * 32 + (r & 7) * 4) * 4);
+            }
+            const bool has0 = A.kind != RSB_OPND_POOLED;
+            const bool has1 = A.kind == RSB_OPND_DUAL_BN_RELU || A.kind == RSB_OPND_AFFINE2 || A.kind == RSB_OPND_POOLED;
+            const float *b0 = A.U, *b1 = A.kind == RSB_OPND_DUAL_BN_RELU ? A.U + A.ku : A.V;
+            const long ld0 = A.ldu, ld1 = A.kind == RSB_OPND_DUAL_BN_RELU ? A.ldu : A.ldv;
+            const bool coef_vec = (A.k0 & 3) == 0 && (A.ku & 3) == 0 && (!A.a || ((uintptr_t)A.a & 15) == 0) &&
+                                  (!A.d || ((uintptr_t)A.d & 15) == 0) && (!A.b || ((uintptr_t)A.b & 15) == 0);
             const long my_tiles = n_row_tiles > blockIdx.x ? (n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-            const int per_tile = P.n_tiles * kc_count;
-            const long total = my_tiles * per_tile;
-            auto issue = [&](long q) {
-                if (q < total) {
-                    const long ti = q / per_tile;
-                    const int kc = (int)(q - ti * per_tile) % kc_count;
-                    const long row_base = (blockIdx.x + ti * gridDim.x) * (long)TM;
-                    const int kl = kc * KC + k4 * 4;
-                    const int nv = min(4, A.K - kl);
-                    float4 *slot = ring + (size_t)(q % RD) * (2 * 4 * PROD_THREADS);
+            const long total = my_tiles * P.n_tiles * kc_count;
+
+            // ---- issue side (runs RD chunks ahead) ----
+            long iq = 0, i_tile = blockIdx.x;
+            int i_nt = 0, i_kc = 0, i_slot = 0;
+            const float *ip0[4], *ip1[4];
+            bool iok[4];
+            auto issue = [&]() {
+                if (iq < total) {
+                    if (i_kc == 0 && i_nt == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const long rr = i_tile * TM + rsub + 32 * j;
+                            iok[j] = rr < P.rows;
+                            const long rs = iok[j] ? rr : 0;
+                            ip0[j] = b0 + rs * ld0;
+                            ip1[j] = has1 ? b1 + rs * ld1 : nullptr;
+                        }
+                    }
+                    const int kl = i_kc * KC + k4 * 4;
+                    const int nv = max(0, min(4, A.K - kl));
+                    const int ks = nv > 0 ? A.k0 + kl : A.k0;
+                    const int k_u = A.kind == RSB_OPND_AFFINE2 ? ks % A.ku : ks;
+                    const uint32_t slot = ring0 + (uint32_t)i_slot * SLOT_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const long row = row_base + rsub + 32 * j;
-                        const bool ok = nv > 0 && row < P.rows;
-                        const float *p0, *p1;
-                        opnd_pieces(A, ok ? row : 0, A.k0 + (nv > 0 ? kl : 0), p0, p1);
-                        if (p0) cp_async16(slot + (0 * 4 + j) * PROD_THREADS + tid, p0, ok ? nv * 4 : 0);
-                        if (p1) cp_async16(slot + (1 * 4 + j) * PROD_THREADS + tid, p1, ok ? nv * 4 : 0);
+                        const int bytes = iok[j] ? nv * 4 : 0;
+                        if (has0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + (uint32_t)j * PIECE_STRIDE), "l"(ip0[j] + k_u), "r"(bytes) : "memory");
+                        if (has1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + (uint32_t)(4 + j) * PIECE_STRIDE), "l"(ip1[j] + ks), "r"(bytes) : "memory");
                     }
+                    if (++i_kc == kc_count) { i_kc = 0; if (++i_nt == P.n_tiles) { i_nt = 0; i_tile += gridDim.x; } }
                 }
                 cp_async_commit();
+                iq++;
+                if (++i_slot == RD) i_slot = 0;
             };
-            for (int p = 0; p < RD; p++) issue(p);
-            for (long q = 0; q < total; q++) {
-                const uint32_t it = (uint32_t)q;
-                const long ti = q / per_tile;
-                const int rem = (int)(q - ti * per_tile);
-                const int nt = rem / kc_count, kc = rem % kc_count;
-                const long row_base = (blockIdx.x + ti * gridDim.x) * (long)TM;
-                const int s = it % STAGES;
-                if (RD == 3) cp_async_wait<RD_MAX - 1>(); else if (RD == 2) cp_async_wait<1>(); else cp_async_wait<0>();
-                mbar_wait(&B->empty[s], ((it / STAGES) & 1) ^ 1);
-                unsigned char *st = smem + (size_t)s * stage_bytes;
-                if (tid == 0) {
-                    mbar_arrive_expect_tx(&B->full[s], (uint32_t)(2 * b_bytes));
-                    const float *src = P.Wp + ((size_t)nt * kc_count + kc) * (2 * (size_t)NT * KC);
-                    bulk_g2s(st + 2 * A_TILE_BYTES, src, (uint32_t)(2 * b_bytes), &B->full[s]);
-                }
-                float *a_hi = reinterpret_cast<float *>(st);
-                float *a_lo = reinterpret_cast<float *>(st + A_TILE_BYTES);
-                const int kl = kc * KC + k4 * 4;
-                const int nv = min(4, A.K - kl);
-                Coef4 cf;
-                if (nv > 0) coef_load(A, A.k0 + kl, nv, cf);
-                const float4 *slot = ring + (size_t)(q % RD) * (2 * 4 * PROD_THREADS);
+            for (int p = 0; p < RD; p++) issue();
+
+            // ---- consume side ----
+            uint32_t it = 0;
+            int c_slot = 0;
+            for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
+                const int nrows = (int)min((long)TM, P.rows - tile * TM);
+                for (int nt = 0; nt < P.n_tiles; nt++) {
+                    for (int kc = 0; kc < kc_count; kc++, it++) {
+                        const int s = it % STAGES;
+                        if (RD == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+                        mbar_wait(&B->empty[s], ((it / STAGES) & 1) ^ 1);
+                        unsigned char *st = smem + (size_t)s * stage_bytes;
+                        if (tid == 0) {
+                            mbar_arrive_expect_tx(&B->full[s], (uint32_t)(2 * b_bytes));
+                            const float *src = P.Wp + ((size_t)nt * kc_count + kc) * (2 * (size_t)NT * KC);
+                            bulk_g2s(st + 2 * A_TILE_BYTES, src, (uint32_t)(2 * b_bytes), &B->full[s]);
+                        }
+                        const uint32_t a_hi = rsb_smem_addr(st), a_lo = a_hi + A_TILE_BYTES;
+                        const int kl = kc * KC + k4 * 4;
+                        const int nv = max(0, min(4, A.K - kl));
+                        const int k = A.k0 + kl;
+                        Coef4 cf;
+                        if (nv == 4 && coef_vec) {
+                            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 a4 = A.a ? __ldg(reinterpret_cast<const float4 *>(A.a + k)) : z4;
+                            const float4 d4 = A.d ? __ldg(reinterpret_cast<const float4 *>(A.d + k)) : z4;
+                            const float4 b4 = A.b ? __ldg(reinterpret_cast<const float4 *>(A.b + k)) : z4;
+                            cf.a[0] = a4.x; cf.a[1] = a4.y; cf.a[2] = a4.z; cf.a[3] = a4.w;
+                            cf.d[0] = d4.x; cf.d[1] = d4.y; cf.d[2] = d4.z; cf.d[3] = d4.w;
+                            cf.b[0] = b4.x; cf.b[1] = b4.y; cf.b[2] = b4.z; cf.b[3] = b4.w;
+                            if (A.kind == RSB_OPND_DUAL_BN_RELU) {
+                                const float4 a24 = __ldg(reinterpret_cast<const float4 *>(A.a + A.ku + k));
+                                const float4 d24 = __ldg(reinterpret_cast<const float4 *>(A.d + A.ku + k));
+                                cf.a2[0] = a24.x; cf.a2[1] = a24.y; cf.a2[2] = a24.z; cf.a2[3] = a24.w;
+                                cf.d2[0] = d24.x; cf.d2[1] = d24.y; cf.d2[2] = d24.z; cf.d2[3] = d24.w;
+                            }
+                        } else if (nv > 0) {
+                            coef_load(A, k, nv, cf);
+                        }
+                        const uint32_t slot = ring0 + (uint32_t)c_slot * SLOT_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int r = rsub + 32 * j;
-                    const long row = row_base + r;
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (nv > 0 && row < P.rows) {
-                        const float4 u4 = slot[(0 * 4 + j) * PROD_THREADS + tid], w4 = slot[(1 * 4 + j) * PROD_THREADS + tid];
-                        const float u[4] = {u4.x, u4.y, u4.z, u4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
-                        long g = 0;
-                        int sidx = 0;
-                        if (A.kind == RSB_OPND_POOLED) { g = row / A.ns; sidx = (int)(row - g * A.ns); }
-                        opnd_apply4(A, cf, u, w, A.k0 + kl, nv, g, sidx, v);
+                        for (int j = 0; j < 4; j++) {
+                            const int r = rsub + 32 * j;
+                            float v[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (nv > 0 && r < nrows) {
+                                float u[4], w[4];
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(u[0]), "=f"(u[1]), "=f"(u[2]), "=f"(u[3]) : "r"(slot + (uint32_t)j * PIECE_STRIDE));
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(slot + (uint32_t)(4 + j) * PIECE_STRIDE));
+                                long g = 0;
+                                int sidx = 0;
+                                if (A.kind == RSB_OPND_POOLED) { const long row = tile * TM + r; g = row / A.ns; sidx = (int)(row - g * A.ns); }
+                                opnd_apply4(A, cf, u, w, k, nv, g, sidx, v);
+                            }
+                            float4 hi, lo;
+                            split4(v, hi, lo);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + st_off[j]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + st_off[j]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+                        }
+                        fence_proxy_async();
+                        mbar_arrive(&B->full[s]);
+                        issue();
+                        if (++c_slot == RD) c_slot = 0;
                     }
-                    float4 hi, lo;
-                    split4(v, hi, lo);
-                    const int off = (r >> 3) * (KC / 4) * 32 + k4 * 32 + (r & 7) * 4;   // floats
-                    *reinterpret_cast<float4 *>(a_hi + off) = hi;
-                    *reinterpret_cast<float4 *>(a_lo + off) = lo;
                 }
-                fence_proxy_async();
-                mbar_arrive(&B->full[s]);
-                issue(q + RD);
             }
             cp_async_wait<0>();
         } else {
@@ -601,6 +650,51 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                             }
                             v[j] = out;
                         }
+                    }
+                    if (E.kind == RSB_EPI_BIAS_STATS) {
+                        // Transpose the warp's 32x32 block through shared memory: lanes become COLUMNS, so every
+                        // store instruction writes one contiguous 128-byte row segment (the TMEM layout gives each
+                        // lane a whole row, which would scatter 32 partial lines per instruction), and the column
+                        // statistics fall out of the same pass.
+#pragma unroll
+                        for (int j = 0; j < 32; j++) my_tile[lane * 33 + j] = v[j];
+                        __syncwarp();
+                        const int n = n0 + lane;
+                        const long rb = tile * TM + q * 32;
+                        float s1 = 0.f, s2 = 0.f;
+                        const int nrows = (E.Y && n < P.N) ? (int)max(0L, min(32L, P.rows - rb)) : 0;
+                        float *ycol = E.Y + (size_t)rb * E.ldy + n;
+                        const float *tcol = my_tile + lane;
+                        if (nrows == 32) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) {
+                                const float t = tcol[i * 33];
+                                s1 += t;
+                                s2 = fmaf(t, t, s2);
+                                *ycol = t;
+                                ycol += E.ldy;
+                            }
+                        } else {
+#pragma unroll 8
+                            for (int i = 0; i < 32; i++) {
+                                const float t = tcol[i * 33];
+                                s1 += t;
+                                s2 = fmaf(t, t, s2);
+                                if (i < nrows) ycol[(size_t)i * E.ldy] = t;
+                            }
+                        }
+                        __syncwarp();
+                        if (E.stats) {
+                            if (reg_stats) {
+#pragma unroll
+                                for (int bi = 0; bi < ACC_BLOCKS; bi++)
+                                    if (bi == (c0 >> 5)) { acc1[bi] += (double)s1; acc2[bi] += (double)s2; }
+                            } else if (n < P.N) {
+                                atomicAdd(E.stats + n, (double)s1);
+                                atomicAdd(E.stats + P.N + n, (double)s2);
+                            }
+                        }
+                        continue;
                     }
                     if (row_ok && E.Y) {
                         float *yrow = E.Y + (size_t)row * E.ldy + n0;
