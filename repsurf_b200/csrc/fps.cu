@@ -231,8 +231,8 @@ FpsPlan fps_plan(int n_max)
     if (n_max <= 256) { pl.cs = 1; pl.nt = 64; }
     else if (n_max <= 1024) { pl.cs = 1; pl.nt = 128; }
     else if (n_max <= 4096) { pl.cs = 1; pl.nt = 256; }
-    else if (n_max <= 8192) { pl.cs = 2; pl.nt = 512; }
-    else if (n_max <= 16384) { pl.cs = 4; pl.nt = 512; }
+    else if (n_max <= 8192) { pl.cs = 1; pl.nt = 512; }     // one CTA: ~0.55 us/sample; any cluster costs >= 0.9 us
+    else if (n_max <= 16384) { pl.cs = 4; pl.nt = 256; }    // measured sweep: profiles/r01_fps_plan_sweep.txt
     else if (n_max <= 65536) { pl.cs = 8; pl.nt = 512; }
     else { pl.cs = 16; pl.nt = 512; }
     const long cap = (long)pl.cs * pl.nt;

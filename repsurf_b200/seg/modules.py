@@ -159,5 +159,7 @@ class UmbrellaSurfaceConstructor(nn.Module):
             feat = umbrella_features(offsets, flip, rotate_key=(self.sort == 'fix'), order="seg")  # [N,k,10]
             n, g, c = feat.shape
             rows = feat.reshape(n * g, c)
+        # (tc.umbrella_mlp runs the same two layers on the tensor-core kernels; at 10 channels the 128 x 32 operand
+        #  tiles are mostly padding and it measured ~1 ms slower per step than these row-matrix GEMMs, so it is off.)
         x = F.relu(bn_rows(linear_rows(rows, self.mlps[0]), self.mlps[1]))
         return linear_rows(x, self.mlps[3]).view(n, g, -1).sum(dim=1)
