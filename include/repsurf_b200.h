@@ -128,6 +128,16 @@ int rsb_interpolation_packed_forward(int n, int c, int k, const float *input, co
 int rsb_interpolation_packed_backward(int n, int c, int k, const float *grad_output, const int *idx,
                                       const float *weight, float *grad_input, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ umbrella surface descriptors (both layouts)
+ * One kernel for group_by_umbrella[_v2] + cal_normal + cal_center + xyz2sphere + cal_const + check_nan_umb
+ * ({classification,segmentation}/modules/{repsurface,recons,polar}_utils.py).  xyz [rows,3]; idx [np,k] kNN lists with
+ * GLOBAL row ids; flip [np] = +-1 per point (the per-cloud random inversion) or NULL; out [np, G, 10] with
+ * G = k - (skip_first ? 1 : 0).  skip_first drops the query itself (classification); rotate_key sorts by the azimuth of
+ * the rotated offsets (segmentation 'fix'); order_seg selects the channel order [polar,normal,pos,centroid] (else
+ * [centroid,polar,normal,pos]). */
+int rsb_umbrella_features(long np, int k, int skip_first, int rotate_key, int order_seg, const float *xyz, const int *idx,
+                          const float *flip, float *out, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ shared MLP on tcgen05 (both layouts)
  * Replaces the library GEMMs behind nn.Conv2d/Conv1d(1x1)/nn.Linear on the RepSurf path
  * (classification/modules/repsurface_utils.py:236-243, segmentation/modules/repsurface_utils.py:220-227,267-282)

@@ -116,18 +116,22 @@ class UmbrellaSurfaceConstructor(nn.Module):
 
     def forward(self, center):
         B, _, N = center.shape
+        N_pts = N
         center_cf = center.contiguous()
         xyz = center_cf.transpose(1, 2).contiguous()
         with torch.no_grad():
-            idx = P.knnquery(self.k, xyz, xyz)[:, :, 1:].contiguous()          # drop the query itself (:119)
-            nbr = P.grouping(center_cf, idx)                                    # [B,3,N,G]
-            offsets = (nbr - center_cf.unsqueeze(-1)).permute(0, 2, 3, 1)       # [B,N,G,3]
+            idx = P.knnquery(self.k, xyz, xyz)                                  # [B,N,k] local ids, self first
             if self.random_inv:
                 # same draw as the reference: CPU generator, one per forward (recons_utils.py:49-51)
-                flip = (torch.randint(0, 2, (B, 1, 1)).float() * 2. - 1.).to(center.device).unsqueeze(-1)
+                sign = (torch.randint(0, 2, (B, 1, 1)).float() * 2. - 1.).to(center.device)
             else:
-                flip = torch.ones(1, 1, 1, 1, device=center.device)
-            feat = umbrella_features(offsets, flip, rotate_key=False, order="cls")   # [B,N,G,10]
+                sign = torch.ones(B, 1, 1, device=center.device)
+            # one kernel: drop the query itself (:119), azimuth sort, triangles, normals, centroids, polar, NaN repair
+            from .. import _native as _nat
+            gidx = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N_pts).view(B, 1, 1)).contiguous()
+            feat = torch.empty(B, N_pts, self.k - 1, 10, device=center.device)
+            _nat.call("rsb_umbrella_features", B * N_pts, self.k, 1, 0, 0, xyz.view(B * N_pts, 3), gidx.view(B * N_pts, self.k),
+                   sign.expand(B, N_pts, 1).reshape(B * N_pts).contiguous(), feat)
             if not self.return_dist:
                 feat = feat[..., :9]
             G, C = feat.shape[2], feat.shape[3]

@@ -60,6 +60,8 @@ struct WgradParams {
     int ldw;
     long rows;
     int M, N, NT, m_tiles, n_tiles, stages;
+    int raw_slots;       // > 0: operands are prefetched with cp.async into a ring of this many raw slabs
+    int raw_slot_bytes;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -898,14 +900,154 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
     if (skip_empty)
         for (size_t i = tid; i < STAGES * stage_bytes / 16; i += THREADS) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
-    const uint32_t tmem_base = cta_prologue(B, tid, warp);
+    const uint32_t tmem_base = cta_prologue(B, tid, warp, P.raw_slots > 0 ? PROD_THREADS + 1 : GROUP_THREADS + 1);
 
     const long n_chunks = (P.rows + KC - 1) / KC;
     // chunks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (my_chunks > 0) {
-        if (warp < PROD_WARPS) {
+        if (warp < PROD_WARPS && P.raw_slots > 0) {
+            // ===== producers, asynchronous path: the raw [32 rows x channels] slabs of both operands are copied
+            // with 16-byte cp.async (a warp per slab row: fully coalesced) into a ring of raw slabs, RD chunks
+            // ahead; the transposing transform then reads shared memory only.
+            const int RS = P.raw_slots, RD = RS - 1;             // RD chunks in flight, one slab being read
+            // per-channel coefficients of both operand tiles live in shared memory for a whole (mt, nt) pass:
+            // [G: a, b, d, a2, d2 | X: a, b, d, a2, d2] x (TM + NT_MAX) channels, filled cooperatively below
+            float *ctab = reinterpret_cast<float *>(B + 1);
+            int *itab = reinterpret_cast<int *>(ctab + 5 * (TM + NT_MAX));        // AFFINE2 wrap: U index per channel
+            unsigned char *ring = reinterpret_cast<unsigned char *>(itab + (TM + NT_MAX));
+            struct Region { const float *base; long ld; int quads, last_bytes, off; };   // off: float4 index in the slab
+            Region Rg[4];
+            int idxmod_g = 0, idxmod_x = 0;                        // AFFINE2 wrap: U index = (k) % ku
+            auto setup = [&](const Opnd &O, int c_base, int width, Region &ra, Region &rb, int &off, int &idxmod) {
+                const int nvalid = max(0, min(width, O.K - c_base));
+                const int quads = (nvalid + 3) / 4, last = (nvalid - 4 * (quads - 1)) * 4;
+                const int k = O.k0 + c_base;
+                ra.base = rb.base = nullptr; ra.quads = rb.quads = 0; ra.ld = rb.ld = 0; ra.last_bytes = rb.last_bytes = 16; ra.off = rb.off = 0;
+                idxmod = 0;
+                if (O.kind == RSB_OPND_AFFINE2) {
+                    const int kk0 = k % O.ku;
+                    const bool wrap = kk0 + nvalid > O.ku;
+                    const int ustart = wrap ? 0 : kk0, uw = wrap ? O.ku : nvalid;
+                    ra.base = O.U + ustart; ra.ld = O.ldu; ra.quads = (uw + 3) / 4; ra.last_bytes = (uw - 4 * (ra.quads - 1)) * 4;
+                    idxmod = wrap ? O.ku : 0;
+                    rb.base = O.V + k; rb.ld = O.ldv; rb.quads = quads; rb.last_bytes = last;
+                } else {
+                    ra.base = O.U + k; ra.ld = O.ldu; ra.quads = quads; ra.last_bytes = last;
+                    if (O.kind == RSB_OPND_DUAL_BN_RELU) { rb.base = O.U + O.ku + k; rb.ld = O.ldu; rb.quads = quads; rb.last_bytes = last; }
+                }
+                ra.off = off; off += KC * ra.quads;
+                rb.off = off; off += KC * rb.quads;
+            };
+            auto copy_chunk = [&](long ci, int slot) {
+                if (ci < my_chunks) {
+                    const long row0 = (blockIdx.x + ci * gridDim.x) * (long)KC;
+                    const uint32_t sb = rsb_smem_addr(ring + (size_t)slot * P.raw_slot_bytes);
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const Region &R = Rg[r];
+                        if (R.quads == 0) continue;
+                        for (int rr = warp; rr < KC; rr += PROD_WARPS) {
+                            const long row = row0 + rr;
+                            const bool ok = row < P.rows;
+                            const float *src = R.base + (ok ? row : 0) * R.ld;
+                            for (int q = lane; q < R.quads; q += 32) {
+                                const int bytes = ok ? (q == R.quads - 1 ? R.last_bytes : 16) : 0;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + (uint32_t)(R.off + rr * R.quads + q) * 16), "l"(src + q * 4), "r"(bytes) : "memory");
+                            }
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+            auto fill_tab = [&](const Opnd &O, int c_base, int width, int idxmod, int t0) {
+                for (int ct = tid; ct < width; ct += PROD_THREADS) {
+                    const int k = O.k0 + c_base + ct;
+                    const bool ok = c_base + ct < O.K;
+                    ctab[0 * (TM + NT_MAX) + t0 + ct] = (ok && O.a) ? __ldg(O.a + k) : 0.f;
+                    ctab[1 * (TM + NT_MAX) + t0 + ct] = (ok && O.b) ? __ldg(O.b + k) : 0.f;
+                    ctab[2 * (TM + NT_MAX) + t0 + ct] = (ok && O.d) ? __ldg(O.d + k) : 0.f;
+                    ctab[3 * (TM + NT_MAX) + t0 + ct] = (ok && O.kind == RSB_OPND_DUAL_BN_RELU) ? __ldg(O.a + O.ku + k) : 0.f;
+                    ctab[4 * (TM + NT_MAX) + t0 + ct] = (ok && O.kind == RSB_OPND_DUAL_BN_RELU) ? __ldg(O.d + O.ku + k) : 0.f;
+                    itab[t0 + ct] = idxmod ? (k % idxmod) : ct;
+                }
+            };
+            auto stage = [&](const Opnd &O, const Region &ra, const Region &rb, int t0, int c_base, int width,
+                             const float *slab, float *hi_base, float *lo_base) {
+                const int k4 = warp;                                  // PROD_WARPS == KC / 4 row quads
+                const int nvalid = max(0, min(width, O.K - c_base));
+                const int nb = skip_empty ? (nvalid + 31) / 32 : (width + 31) / 32;
+                for (int cbk = 0; cbk < nb; cbk++) {
+                    const int ct = cbk * 32 + lane;
+                    if (ct >= width) break;
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (ct < nvalid) {
+                        const float a = ctab[0 * (TM + NT_MAX) + t0 + ct], b = ctab[1 * (TM + NT_MAX) + t0 + ct];
+                        const float d = ctab[2 * (TM + NT_MAX) + t0 + ct];
+                        const float a2 = ctab[3 * (TM + NT_MAX) + t0 + ct], d2 = ctab[4 * (TM + NT_MAX) + t0 + ct];
+                        const int iu = itab[t0 + ct];
+                        const float *pa = slab + (size_t)ra.off * 4 + (size_t)(k4 * 4) * ra.quads * 4 + iu;
+                        const float *pb = slab + (size_t)rb.off * 4 + (size_t)(k4 * 4) * rb.quads * 4 + ct;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float u = pa[(size_t)e * ra.quads * 4];
+                            const float w = rb.quads ? pb[(size_t)e * rb.quads * 4] : 0.f;
+                            switch (O.kind) {
+                            case RSB_OPND_RAW: v[e] = u; break;
+                            case RSB_OPND_BN_RELU: v[e] = fmaxf(fmaf(u, a, d), 0.f); break;
+                            case RSB_OPND_DUAL_BN_RELU: v[e] = fmaxf(fmaf(u, a, d) + fmaf(w, a2, d2), 0.f); break;
+                            default: v[e] = fmaf(a, u, fmaf(b, w, d)); break;
+                            }
+                        }
+                    }
+                    float4 hi, lo;
+                    split4(v, hi, lo);
+                    const int off = (ct >> 3) * (KC / 4) * 32 + k4 * 32 + (ct & 7) * 4;   // floats
+                    *reinterpret_cast<float4 *>(hi_base + off) = hi;
+                    *reinterpret_cast<float4 *>(lo_base + off) = lo;
+                }
+            };
+            uint32_t it = 0;
+            for (int mt = 0; mt < P.m_tiles; mt++)
+                for (int nt = 0; nt < P.n_tiles; nt++) {
+                    int off = 0;
+                    setup(P.G, mt * TM, TM, Rg[0], Rg[1], off, idxmod_g);
+                    setup(P.X, nt * NT, NT, Rg[2], Rg[3], off, idxmod_x);
+                    fill_tab(P.G, mt * TM, TM, idxmod_g, 0);
+                    fill_tab(P.X, nt * NT, NT, idxmod_x, TM);
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");
+                    int islot = 0, cslot = 0;
+                    for (int p = 0; p < RD; p++) { copy_chunk(p, islot); if (++islot == RS) islot = 0; }
+                    for (long ci = 0; ci < my_chunks; ci++, it++) {
+                        switch (RD) {   // wait until at most RD-1 younger slabs are still in flight
+                        case 7: cp_async_wait<6>(); break;
+                        case 6: cp_async_wait<5>(); break;
+                        case 5: cp_async_wait<4>(); break;
+                        case 4: cp_async_wait<3>(); break;
+                        case 3: cp_async_wait<2>(); break;
+                        case 2: cp_async_wait<1>(); break;
+                        default: cp_async_wait<0>(); break;
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");   // slab ci complete; slab ci-1 no longer read
+                        copy_chunk(ci + RD, islot);
+                        if (++islot == RS) islot = 0;
+                        const int s = it % STAGES;
+                        mbar_wait(&B->empty[s], ((it / STAGES) & 1) ^ 1);
+                        unsigned char *st = smem + (size_t)s * stage_bytes;
+                        const float *slab = reinterpret_cast<const float *>(ring + (size_t)cslot * P.raw_slot_bytes);
+                        stage(P.G, Rg[0], Rg[1], 0, mt * TM, TM, slab, reinterpret_cast<float *>(st), reinterpret_cast<float *>(st + a_bytes));
+                        stage(P.X, Rg[2], Rg[3], TM, nt * NT, NT, slab, reinterpret_cast<float *>(st + 2 * a_bytes),
+                              reinterpret_cast<float *>(st + 2 * a_bytes + b_bytes));
+                        fence_proxy_async();
+                        mbar_arrive(&B->full[s]);
+                        if (tid == 0) mbar_arrive(&B->full[s]);
+                        if (++cslot == RS) cslot = 0;
+                    }
+                    cp_async_wait<0>();
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");
+                }
+        } else if (warp < PROD_WARPS) {
             const int grp = warp >> 2, w4 = warp & 3;
             uint32_t it = 0;
             for (int mt = 0; mt < P.m_tiles; mt++)
@@ -1124,10 +1266,53 @@ RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *
     P.m_tiles = (P.M + TM - 1) / TM;
     P.n_tiles = (P.N + P.NT - 1) / P.NT;
     const size_t stage_b = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)P.NT * KC * 4;
-    P.stages = (int)((227 * 1024 - sizeof(Barriers) - 1024) / stage_b);
+    const size_t tab_b = 6 * (size_t)(TM + NT_MAX) * 4;      // coefficient / index tables of the asynchronous path
+    const size_t budget = 227 * 1024 - sizeof(Barriers) - 1024 - tab_b;
+    // asynchronous prefetch: every piece must be 16-byte aligned; POOLED operands stay on the synchronous path
+    auto aligned = [](const rsb_opnd_t *O) {
+        if (O->kind == RSB_OPND_POOLED) return false;
+        if ((O->ldu % 4) || ((uintptr_t)O->U % 16) || (O->k0 % 4)) return false;
+        if ((O->kind == RSB_OPND_DUAL_BN_RELU || O->kind == RSB_OPND_AFFINE2) && (O->ku % 4)) return false;
+        if (O->kind == RSB_OPND_AFFINE2 && ((O->ldv % 4) || ((uintptr_t)O->V % 16))) return false;
+        return true;
+    };
+    // float4 per slab row of one operand tile — the same arithmetic as the kernel's setup()
+    auto tile_quads = [](const rsb_opnd_t *O, int c_base, int width) {
+        int nvalid = O->K - c_base;
+        if (nvalid > width) nvalid = width;
+        if (nvalid < 0) nvalid = 0;
+        const int quads = (nvalid + 3) / 4;
+        if (O->kind == RSB_OPND_DUAL_BN_RELU) return 2 * quads;
+        if (O->kind == RSB_OPND_AFFINE2) {
+            const int kk0 = (O->k0 + c_base) % O->ku;
+            const int uw = (kk0 + nvalid > O->ku) ? O->ku : nvalid;
+            return quads + (uw + 3) / 4;
+        }
+        return quads;
+    };
+    int max_quads = 0;
+    for (int mt = 0; mt < P.m_tiles; mt++)
+        for (int nt = 0; nt < P.n_tiles; nt++) {
+            const int q = tile_quads(G, mt * TM, TM) + tile_quads(X, nt * P.NT, P.NT);
+            if (q > max_quads) max_quads = q;
+        }
+    P.raw_slots = 0;
+    P.raw_slot_bytes = 0;
+    P.stages = (int)(budget / stage_b);
+    if (aligned(G) && aligned(X) && !getenv("RSB_TC_SYNC")) {
+        const size_t slot = (size_t)KC * 16 * max_quads;
+        // two operand stages are enough once loads are decoupled; spend the rest of shared memory on ring depth
+        if (budget >= 2 * stage_b + 3 * slot) {
+            int rs = (int)((budget - 2 * stage_b) / slot);
+            if (rs > 8) rs = 8;
+            P.raw_slots = rs;
+            P.raw_slot_bytes = (int)slot;
+            P.stages = (int)((budget - (size_t)rs * slot) / stage_b);
+        }
+    }
     if (P.stages > STAGES_MAX) P.stages = STAGES_MAX;
     RSB_REQUIRE(P.stages >= 2, "tile does not fit");
-    const size_t smem = P.stages * stage_b + sizeof(Barriers) + 1024;
+    const size_t smem = P.stages * stage_b + sizeof(Barriers) + 1024 + tab_b + (size_t)P.raw_slots * P.raw_slot_bytes;
     static bool attr_set = false;
     if (!attr_set) {
         RSB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -146,17 +146,25 @@ class UmbrellaSurfaceConstructor(nn.Module):
         with torch.no_grad():
             # all k neighbours are kept, the query itself included (the reference takes no [:, 1:] slice)
             idx, _ = P.knnquery(self.k, center, center, offset, offset)
-            offsets = P.grouping(center, idx) - center.unsqueeze(1)         # [N,k,3]
             if self.random_inv:
                 # same draw as the reference: numpy global RNG, one value per cloud (recons_utils.py:28-37)
                 keep = np.random.rand(offset.shape[0]) < 0.5
                 sizes = P._sizes(P.host_offsets(offset))
                 sign = torch.from_numpy(np.where(keep, 1.0, -1.0).astype(np.float32)).to(center.device, non_blocking=True)
                 flip = torch.repeat_interleave(sign, torch.tensor(sizes, device=center.device),
-                                               output_size=center.shape[0]).view(-1, 1, 1)
+                                               output_size=center.shape[0])
             else:
-                flip = torch.ones(1, 1, 1, device=center.device)
-            feat = umbrella_features(offsets, flip, rotate_key=(self.sort == 'fix'), order="seg")  # [N,k,10]
+                flip = None
+            if center.is_cuda:
+                # one kernel: azimuth sort, triangles, normals, centroids, polar form, plane constant, NaN repair
+                from .. import _native as N
+                feat = torch.empty(center.shape[0], self.k, 10, device=center.device)
+                N.call("rsb_umbrella_features", center.shape[0], self.k, 0, 1 if self.sort == 'fix' else 0, 1,
+                       center.contiguous(), idx, flip, feat)
+            else:
+                offsets = center[idx.long()] - center.unsqueeze(1)
+                fl = flip.view(-1, 1, 1) if flip is not None else torch.ones(1, 1, 1)
+                feat = umbrella_features(offsets, fl, rotate_key=(self.sort == 'fix'), order="seg")
             n, g, c = feat.shape
             rows = feat.reshape(n * g, c)
         # (tc.umbrella_mlp runs the same two layers on the tensor-core kernels; at 10 channels the 128 x 32 operand

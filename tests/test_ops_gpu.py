@@ -331,3 +331,28 @@ def test_knn_grid_lattice_and_degenerate_inputs(monkeypatch):
     widx, _ = O.knn_packed(9, few, few, off2, off2)
     gidx, _ = P.knnquery(9, few.to(cuda), few.to(cuda), off2.to(cuda), off2.to(cuda))
     assert torch.equal(gidx.cpu(), widx)
+
+
+# ------------------------------------------------------------------------------------------- fused umbrella geometry
+@pytest.mark.parametrize("order,rotate,skip", [("seg", True, False), ("cls", False, True)])
+def test_umbrella_kernel_matches_tensor_formulation(order, rotate, skip):
+    """csrc/umbrella.cu vs repsurf_b200.geometry.umbrella_features (the vectorised restatement that the golden
+    model tests pin to the reference).  Points whose neighbour azimuths tie within an ulp may sort differently."""
+    from repsurf_b200 import _native as N
+    from repsurf_b200.geometry import umbrella_features
+    P = _seg()
+    g = torch.Generator().manual_seed(41)
+    n, k = 6000, 9
+    xyz = (torch.rand(n, 3, generator=g) * torch.tensor([4.0, 4.0, 2.0])).to(cuda)
+    off = torch.tensor([2500, 6000], dtype=torch.int32, device=cuda)
+    idx, _ = P.knnquery(k, xyz, xyz, off, off)
+    flip = (torch.randint(0, 2, (n,), generator=g).float() * 2 - 1).to(cuda)
+    G = k - (1 if skip else 0)
+    out = torch.empty(n, G, 10, device=cuda)
+    N.call("rsb_umbrella_features", n, k, 1 if skip else 0, 1 if rotate else 0, 1 if order == "seg" else 0, xyz, idx, flip, out)
+    nb = idx[:, 1:] if skip else idx
+    offsets = xyz[nb.long()] - xyz[:, None]
+    want = umbrella_features(offsets, flip.view(-1, 1, 1), rotate_key=rotate, order=order)
+    err = (out - want).abs().amax(dim=(1, 2)) / want.abs().max()
+    assert (err > 1e-5).float().mean().item() < 2e-3
+    assert not torch.isnan(out).any() or torch.isnan(want).any()
