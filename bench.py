@@ -403,11 +403,19 @@ def main():
                 rooflines[name] = {"kernel": "knn_grid_kernel", "bound": "fp32 (all-pairs model: 9 flop/pair)", "achieved": ach,
                                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "launch_ms": t_ms, "launch": note,
                                    "algorithmic_pairs_per_launch": pairs}
-    roof = None
-    if dom and dom[0] in rooflines:
-        roof = dict(rooflines[dom[0]])
-        roof["traffic"] = None
-        roof["peak_source"] = peak_src
+    # measured DRAM traffic per launch from the committed ncu --set full capture of the same kernels
+    # (profiles/r01_ncu_full_seg_traffic.json, produced by scripts/ncu_summary.py; seg workload shapes)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_seg_traffic.json")
+    if os.path.exists(tpath) and args.workload == "seg":
+        traffic = json.load(open(tpath))
+    fam = {"rsb_gemm_wgrad": "gemm_wgrad_kernel", "rsb_gemm_rows": "gemm_rows_kernel", "rsb_knnquery_grid": "knn_grid_kernel",
+           "rsb_furthestsampling_packed": "fps_kernel", "rsb_furthestsampling_dense": "fps_kernel"}
+    for name, r in rooflines.items():
+        t = traffic.get(fam.get(name, ""))
+        r["traffic"] = t["dram_bytes"] if t else None
+        r["peak_source"] = peak_src
+    roof = dict(rooflines[dom[0]]) if dom and dom[0] in rooflines else None
 
     out = {
         "metric": metric, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
