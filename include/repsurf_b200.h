@@ -128,6 +128,16 @@ int rsb_interpolation_packed_forward(int n, int c, int k, const float *input, co
 int rsb_interpolation_packed_backward(int n, int c, int k, const float *grad_output, const int *idx,
                                       const float *weight, float *grad_input, cudaStream_t stream);
 
+/* Row-matrix builder of a grouped level (input of the fused shared MLP), one pass, and its backward scatter:
+ *   rows[r] = [xyz[idx[r]] - new_xyz[r/ns] (+ polar form) | pad to P4 | normal[idx[r]] (Cn) | feature[idx[r]] (Cf) | pad to ld]
+ * idx [rows] GLOBAL row ids; replaces the gathers + subtraction + xyz2sphere + cat of
+ * segmentation/modules/repsurface_utils.py:36-49 and classification/modules/repsurface_utils.py:37-57. */
+int rsb_group_rows_forward(long rows, int ns, int polar, int P4, int Cn, int Cf, int ld, const float *xyz,
+                           const float *new_xyz, const int *idx, const float *normal, const float *feature, float *out,
+                           cudaStream_t stream);
+int rsb_group_rows_backward(long rows, int P4, int Cn, int Cf, int ld, const float *drows, const int *idx, float *dnormal,
+                            float *dfeature, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ umbrella surface descriptors (both layouts)
  * One kernel for group_by_umbrella[_v2] + cal_normal + cal_center + xyz2sphere + cal_const + check_nan_umb
  * ({classification,segmentation}/modules/{repsurface,recons,polar}_utils.py).  xyz [rows,3]; idx [np,k] kNN lists with

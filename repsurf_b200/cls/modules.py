@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from . import pointops as P
 from ..seg import pointops as PP
 from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, linear_rows, pack_rows, sa_mlp
+from ..mlp import bn_rows, group_rows, linear_rows, pack_rows, sa_mlp
 
 
 def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_normal, return_polar):
@@ -37,6 +37,13 @@ def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_
     idx = P.ballquery(radius, nsample, xyz, new_xyz)                    # [B,m,ns] local ids
     gidx = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N).view(B, 1, 1)).view(B * npoint, nsample)
     R = B * npoint * nsample
+    if (feature is None or return_normal):
+        # one kernel builds the packed row matrix [rel xyz, polar | normal | feature]
+        rows, layout = group_rows(xyz.view(B * N, 3), new_xyz.view(B * npoint, 3), gidx,
+                                  normal.transpose(1, 2).reshape(B * N, -1),
+                                  feature.transpose(1, 2).reshape(B * N, -1) if feature is not None else None,
+                                  nsample, return_polar)
+        return new_xyz.transpose(1, 2).contiguous(), new_normal, rows, layout
     rel = PP.grouping(xyz.view(B * N, 3), gidx) - new_xyz.view(B * npoint, 1, 3)       # [B*m,ns,3]
     pos = torch.cat([rel, xyz2sphere(rel)], dim=-1) if return_polar else rel
     feats = []

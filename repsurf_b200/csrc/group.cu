@@ -159,6 +159,66 @@ __global__ void __launch_bounds__(TPB) packed_interp_bwd(long n, int c, int k, c
     }
 }
 
+// Row-matrix builder of one grouped level (the input of the fused shared MLP), one pass:
+//   rows[r, :] = [ xyz[idx[r]] - new_xyz[r / ns]  (+ its polar form when `polar`) | 0-pad to P4 |
+//                  normal[idx[r], :Cn] | feature[idx[r], :Cf] | 0-pad to ld ]
+// replaces the reference's three index gathers + subtraction + xyz2sphere + cat + transpose().contiguous()
+// (segmentation/modules/repsurface_utils.py:36-49, classification/modules/repsurface_utils.py:37-57).
+__global__ void __launch_bounds__(TPB) group_rows_fwd(long rows, int ns, int polar, int P4, int Cn, int Cf, int ld,
+                                                      const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                                                      const int *__restrict__ idx, const float *__restrict__ normal,
+                                                      const float *__restrict__ feature, float *__restrict__ out)
+{
+    const long total = rows * ld;
+    for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
+        const long r = i / ld;
+        const int c = (int)(i - r * ld);
+        const int src = __ldg(idx + r);
+        float v = 0.f;
+        if (c < P4) {
+            const int P = polar ? 6 : 3;
+            if (c < P) {
+                const float *q = new_xyz + (r / ns) * 3;
+                const float dx = __ldg(xyz + (size_t)src * 3) - __ldg(q), dy = __ldg(xyz + (size_t)src * 3 + 1) - __ldg(q + 1),
+                            dz = __ldg(xyz + (size_t)src * 3 + 2) - __ldg(q + 2);
+                if (c == 0) v = dx;
+                else if (c == 1) v = dy;
+                else if (c == 2) v = dz;
+                else {
+                    const float rho = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                    if (c == 3) v = rho;
+                    // torch divides by a host scalar as a multiplication by its fp32 reciprocal, in separate roundings
+                    else if (c == 4) v = rho == 0.f ? 0.f : __fmul_rn(acosf(__fdiv_rn(dz, rho)), 1.0f / 3.14159265358979323846f);
+                    else v = __fadd_rn(__fmul_rn(atan2f(dy, dx), 1.0f / 6.28318530717958647692f), 0.5f);
+                }
+            }
+        } else if (c < P4 + Cn) {
+            v = __ldg(normal + (size_t)src * Cn + (c - P4));
+        } else if (c < P4 + Cn + Cf) {
+            v = __ldg(feature + (size_t)src * Cf + (c - P4 - Cn));
+        }
+        out[i] = v;
+    }
+}
+
+// scatter-add of the feature columns of d(rows) back to the per-point tensors (fp32 atomics, like the reference's
+// grouping backward: order-dependent sums, rule R6)
+__global__ void __launch_bounds__(TPB) group_rows_bwd(long rows, int P4, int Cn, int Cf, int ld, const float *__restrict__ drows,
+                                                      const int *__restrict__ idx, float *__restrict__ dnormal,
+                                                      float *__restrict__ dfeature)
+{
+    const int C = Cn + Cf;
+    const long total = rows * C;
+    for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
+        const long r = i / C;
+        const int c = (int)(i - r * C);
+        const float g = __ldg(drows + (size_t)r * ld + P4 + c);
+        const int src = __ldg(idx + r);
+        if (c < Cn) { if (dnormal) atomicAdd(dnormal + (size_t)src * Cn + c, g); }
+        else if (dfeature) atomicAdd(dfeature + (size_t)src * Cf + (c - Cn), g);
+    }
+}
+
 }  // namespace
 
 #define RSB_LAUNCH_1D(kern, work, ...)                                         \
@@ -248,5 +308,21 @@ RSB_EXPORT int rsb_interpolation_packed_backward(int n, int c, int k, const floa
                                                  const float *weight, float *grad_input, cudaStream_t stream)
 {
     RSB_LAUNCH_1D(packed_interp_bwd, (long)n * c, (long)n, c, k, grad_output, idx, weight, grad_input);
+    return 0;
+}
+
+RSB_EXPORT int rsb_group_rows_forward(long rows, int ns, int polar, int P4, int Cn, int Cf, int ld, const float *xyz,
+                                      const float *new_xyz, const int *idx, const float *normal, const float *feature,
+                                      float *out, cudaStream_t stream)
+{
+    RSB_REQUIRE(P4 >= (polar ? 6 : 3) && ld >= P4 + Cn + Cf, "bad column layout");
+    RSB_LAUNCH_1D(group_rows_fwd, rows * ld, rows, ns, polar, P4, Cn, Cf, ld, xyz, new_xyz, idx, normal, feature, out);
+    return 0;
+}
+
+RSB_EXPORT int rsb_group_rows_backward(long rows, int P4, int Cn, int Cf, int ld, const float *drows, const int *idx,
+                                       float *dnormal, float *dfeature, cudaStream_t stream)
+{
+    RSB_LAUNCH_1D(group_rows_bwd, rows * (Cn + Cf), rows, P4, Cn, Cf, ld, drows, idx, dnormal, dfeature);
     return 0;
 }

@@ -1319,7 +1319,12 @@ RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *
         attr_set = true;
     }
     const long n_chunks = (rows + KC - 1) / KC;
-    const int grid = (int)(n_chunks < rsb_sm_count() ? n_chunks : rsb_sm_count());
+    // every CTA flushes its whole dW tile with atomics: give each at least 2 chunks of reduction first
+    // (swept 1/2/4/8/16 on the S3DIS step: 12.14 / 12.06 / 12.16 / 12.58 / 14.25 ms of wgrad time)
+    static const int min_chunks = getenv("RSB_WGRAD_MINCHUNKS") ? atoi(getenv("RSB_WGRAD_MINCHUNKS")) : 2;
+    long want = (n_chunks + min_chunks - 1) / min_chunks;
+    if (want < 1) want = 1;
+    const int grid = (int)(want < rsb_sm_count() ? want : rsb_sm_count());
     gemm_wgrad_kernel<<<grid, THREADS, smem, stream>>>(P);
     RSB_CHECK_LAUNCH("gemm_wgrad_kernel");
     RSB_COUNT_LAUNCH(1);

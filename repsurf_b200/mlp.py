@@ -43,6 +43,47 @@ def pack_rows(pos, feats):
     return torch.cat(parts, dim=-1), P4, F_
 
 
+class _GroupRows(torch.autograd.Function):
+    """Fused builder of the packed row matrix of a grouped level (csrc/group.cu group_rows_*)."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, idx, normal, feature, ns, polar):
+        from . import _native as N
+        rows = idx.numel()
+        P = 6 if polar else 3
+        P4 = (P + 3) // 4 * 4
+        Cn = normal.shape[1]
+        Cf = feature.shape[1] if feature is not None else 0
+        ld = P4 + (Cn + Cf + 3) // 4 * 4
+        out = torch.empty(rows, ld, device=xyz.device)
+        normal = normal.contiguous()
+        feature = feature.contiguous() if feature is not None else None
+        N.call("rsb_group_rows_forward", rows, ns, 1 if polar else 0, P4, Cn, Cf, ld, xyz.contiguous(), new_xyz.contiguous(),
+               idx, normal, feature, out)
+        ctx.save_for_backward(idx)
+        ctx.dims = (rows, P4, Cn, Cf, ld, normal.shape[0], feature is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, drows):
+        from . import _native as N
+        idx, = ctx.saved_tensors
+        rows, P4, Cn, Cf, ld, n, has_f = ctx.dims
+        dn = torch.zeros(n, Cn, device=drows.device) if ctx.needs_input_grad[3] else None
+        df = torch.zeros(n, Cf, device=drows.device) if (has_f and ctx.needs_input_grad[4]) else None
+        if dn is not None or df is not None:
+            N.call("rsb_group_rows_backward", rows, P4, Cn, Cf, ld, drows.contiguous(), idx, dn, df)
+        return None, None, None, dn, df, None, None
+
+
+def group_rows(xyz, new_xyz, idx, normal, feature, nsample, polar):
+    """rows [M*ns, ld], layout (P4, Cn+Cf) — one kernel instead of three gathers + sub (+ polar) + cat + pad.
+    xyz [n,3], new_xyz [M,3], idx [M,ns] GLOBAL row ids, normal [n,Cn], feature [n,Cf] | None."""
+    rows = _GroupRows.apply(xyz, new_xyz, idx.reshape(-1).contiguous(), normal, feature, nsample, polar)
+    P4 = 8 if polar else 4
+    return rows, (P4, normal.shape[1] + (feature.shape[1] if feature is not None else 0))
+
+
 def sa_mlp(rows, pos_channel, mod, nsample, layout=None):
     """Shared MLP + max-pool of a SurfaceAbstractionCD level.  Training mode runs the fused tcgen05 path
     (repsurf_b200.tc: 3xTF32 GEMMs with BatchNorm/ReLU/pool folded into operand loads and epilogues, hand-written

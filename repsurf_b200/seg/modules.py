@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import pointops as P
 from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, linear_rows, pack_rows, sa_mlp
+from ..mlp import bn_rows, group_rows, linear_rows, pack_rows, sa_mlp
 
 
 def strided_offsets(offset, stride):
@@ -50,6 +50,9 @@ def _sample_and_group(stride, nsample, center, normal, feature, offset, return_p
         new_center, new_normal, new_offset = center, normal, offset
     group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
     M = new_center.shape[0]
+    if center.is_cuda:
+        rows, layout = group_rows(center, new_center, group_idx, normal, feature, nsample, return_polar)
+        return new_center, new_normal, rows, layout, new_offset
     rel = P.grouping(center, group_idx) - new_center.unsqueeze(1)
     pos = torch.cat([rel, xyz2sphere(rel)], dim=-1) if return_polar else rel
     feats = [P.grouping(normal.contiguous(), group_idx).view(M * nsample, -1)]

@@ -356,3 +356,44 @@ def test_umbrella_kernel_matches_tensor_formulation(order, rotate, skip):
     err = (out - want).abs().amax(dim=(1, 2)) / want.abs().max()
     assert (err > 1e-5).float().mean().item() < 2e-3
     assert not torch.isnan(out).any() or torch.isnan(want).any()
+
+
+# ------------------------------------------------------------------------------------------- fused row builder
+@pytest.mark.parametrize("polar,cf", [(True, 0), (True, 64), (False, 32)])
+def test_group_rows_matches_gather_composition(polar, cf):
+    """csrc/group.cu group_rows_* vs the reference's composition (gathers, subtraction, xyz2sphere, cat:
+    segmentation/modules/repsurface_utils.py:36-49): gathers and relative xyz bit-exact, polar columns to an ulp of
+    the libdevice functions, backward scatter against an fp64 index_add."""
+    from repsurf_b200.geometry import xyz2sphere
+    from repsurf_b200.mlp import group_rows
+    g = torch.Generator().manual_seed(43)
+    n, M, ns, cn = 5000, 700, 24, 10
+    xyz = torch.rand(n, 3, generator=g).to(cuda)
+    new_xyz = xyz[torch.randperm(n, generator=g)[:M].to(cuda)].contiguous()
+    idx = torch.randint(0, n, (M, ns), generator=g, dtype=torch.int32).to(cuda)
+    idx[:, 0] = torch.arange(M, device=cuda, dtype=torch.int32)          # some zero-length offsets (rho == 0)
+    new_xyz[:] = xyz[:M]
+    normal = torch.randn(n, cn, generator=g).to(cuda).requires_grad_()
+    feat = torch.randn(n, cf, generator=g).to(cuda).requires_grad_() if cf else None
+    rows, (P4, F) = group_rows(xyz, new_xyz, idx, normal, feat, ns, polar)
+    rel = xyz[idx.long()] - new_xyz[:, None]
+    pos = torch.cat([rel, xyz2sphere(rel)], -1) if polar else rel
+    P = pos.shape[-1]
+    rows3 = rows.view(M, ns, -1)
+    assert torch.equal(rows3[..., :3], rel)
+    if polar:
+        err = (rows3[..., 3:P] - pos[..., 3:]).abs().amax(dim=(0, 1))
+        assert (err < 2e-6).all(), err       # torch's CUDA sqrt is not the IEEE one (<= 1 ulp), acos amplifies it
+    assert (rows3[..., P:P4] == 0).all() and F == cn + cf
+    assert torch.equal(rows3[..., P4:P4 + cn], normal[idx.long()])
+    if cf:
+        assert torch.equal(rows3[..., P4 + cn:P4 + F], feat[idx.long()])
+    assert (rows3[..., P4 + F:] == 0).all()
+    w = torch.randn(rows.shape, generator=torch.Generator().manual_seed(1)).to(cuda)
+    (rows * w).sum().backward()
+    w3 = w.view(M, ns, -1).double()
+    want = torch.zeros(n, cn, dtype=torch.float64, device=cuda).index_add_(0, idx.view(-1).long(), w3[..., P4:P4 + cn].reshape(-1, cn))
+    assert torch.allclose(normal.grad.double(), want, rtol=1e-5, atol=1e-5)
+    if cf:
+        want = torch.zeros(n, cf, dtype=torch.float64, device=cuda).index_add_(0, idx.view(-1).long(), w3[..., P4 + cn:P4 + F].reshape(-1, cf))
+        assert torch.allclose(feat.grad.double(), want, rtol=1e-5, atol=1e-5)
