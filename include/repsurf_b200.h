@@ -138,6 +138,11 @@ int rsb_group_rows_forward(long rows, int ns, int polar, int P4, int Cn, int Cf,
 int rsb_group_rows_backward(long rows, int P4, int Cn, int Cf, int ld, const float *drows, const int *idx, float *dnormal,
                             float *dfeature, cudaStream_t stream);
 
+/* per-segment min / max of packed values [n]; vmin / vmax [b] must be pre-set to +inf / -inf (exact, order-free).
+ * Device replacement of the per-cloud .min()/.max() of the sector split, pointops.py:70-71. */
+int rsb_segment_minmax(int b, long n_max, const float *values, const int *offset, float *vmin, float *vmax,
+                       cudaStream_t stream);
+
 /* ------------------------------------------------------------------ umbrella surface descriptors (both layouts)
  * One kernel for group_by_umbrella[_v2] + cal_normal + cal_center + xyz2sphere + cal_const + check_nan_umb
  * ({classification,segmentation}/modules/{repsurface,recons,polar}_utils.py).  xyz [rows,3]; idx [np,k] kNN lists with
@@ -147,6 +152,22 @@ int rsb_group_rows_backward(long rows, int P4, int Cn, int Cf, int ld, const flo
  * [centroid,polar,normal,pos]). */
 int rsb_umbrella_features(long np, int k, int skip_first, int rotate_key, int order_seg, const float *xyz, const int *idx,
                           const float *flip, float *out, cudaStream_t stream);
+
+/* Umbrella MLP of the segmentation tree, Conv1d(10,10) + BatchNorm(train) + ReLU + Conv1d(10,10) + sum over the g
+ * triangles of a point (segmentation/modules/repsurface_utils.py:297-302, :322-327), fused and recomputing: only the
+ * rows X [rows, 10] and the output [rows/g, 10] touch HBM.  cin == c == 10 (anything else is refused).
+ *   _stats   : stats[0..c) += column sums of Y1 = X W1^T + b1, stats[c..2c) += sums of squares (-> rsb_bn_finalize)
+ *   _forward : out[p] = sum_{j<g} W2 relu(sc*Y1 + sh) + b2; g <= 256
+ *   _backward: acc1 [c*c + 3c] += (dW2 | db2 | sum dZ = dbeta | sum dZ*xhat = dgamma), acc2 [c*cin + c] += (dW1 | db1);
+ *              both zeroed by the caller, fp64.  train = 0: BatchNorm used fixed (running) statistics. */
+int rsb_umbrella_mlp_stats(long rows, int cin, int c, const float *X, const float *W1, const float *b1, double *stats,
+                           cudaStream_t stream);
+int rsb_umbrella_mlp_forward(long rows, int g, int cin, int c, const float *X, const float *W1, const float *b1,
+                             const float *W2, const float *b2, const float *sc, const float *sh, float *out,
+                             cudaStream_t stream);
+int rsb_umbrella_mlp_backward(long rows, int g, int cin, int c, int train, const float *X, const float *dOut, const float *W1,
+                              const float *b1, const float *W2, const float *sc, const float *sh, const float *mu,
+                              const float *inv, double *acc1, double *acc2, cudaStream_t stream);
 
 /* ------------------------------------------------------------------ shared MLP on tcgen05 (both layouts)
  * Replaces the library GEMMs behind nn.Conv2d/Conv1d(1x1)/nn.Linear on the RepSurf path

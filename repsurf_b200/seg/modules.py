@@ -153,8 +153,11 @@ class UmbrellaSurfaceConstructor(nn.Module):
                 # same draw as the reference: numpy global RNG, one value per cloud (recons_utils.py:28-37)
                 keep = np.random.rand(offset.shape[0]) < 0.5
                 sizes = P._sizes(P.host_offsets(offset))
-                sign = torch.from_numpy(np.where(keep, 1.0, -1.0).astype(np.float32)).to(center.device, non_blocking=True)
-                flip = torch.repeat_interleave(sign, torch.tensor(sizes, device=center.device),
+                sign = torch.from_numpy(np.where(keep, 1.0, -1.0).astype(np.float32))
+                if center.is_cuda:
+                    sign = sign.pin_memory()
+                sign = sign.to(center.device, non_blocking=True)
+                flip = torch.repeat_interleave(sign, P.const_tensor(sizes, torch.int64, center.device),
                                                output_size=center.shape[0])
             else:
                 flip = None
@@ -170,7 +173,9 @@ class UmbrellaSurfaceConstructor(nn.Module):
                 feat = umbrella_features(offsets, fl, rotate_key=(self.sort == 'fix'), order="seg")
             n, g, c = feat.shape
             rows = feat.reshape(n * g, c)
-        # (tc.umbrella_mlp runs the same two layers on the tensor-core kernels; at 10 channels the 128 x 32 operand
-        #  tiles are mostly padding and it measured ~1 ms slower per step than these row-matrix GEMMs, so it is off.)
+        if feat.is_cuda and c == 10 and self.mlps[0].weight.shape[0] == 10 and g <= 256:
+            # both 10-channel layers, the BatchNorm, the ReLU and the sum over triangles in recomputing SIMT kernels
+            from ..tc import umbrella_mlp_fused
+            return umbrella_mlp_fused(feat, self.mlps[0], self.mlps[1], self.mlps[3])
         x = F.relu(bn_rows(linear_rows(rows, self.mlps[0]), self.mlps[1]))
         return linear_rows(x, self.mlps[3]).view(n, g, -1).sum(dim=1)

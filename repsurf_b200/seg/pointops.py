@@ -44,9 +44,27 @@ def host_offsets(t):
     return vals
 
 
+_CONST = {}
+
+
+def const_tensor(values, dtype, device):
+    """Device copy of a small host list, cached by value and never written to.  torch.tensor(..., device=cuda)
+    synchronises the stream on every call (pageable host-to-device copy); a training loop over a fixed batch layout
+    would drain the launch queue a dozen times per step.  First use stages through pinned memory, asynchronously."""
+    key = (tuple(values), dtype, str(device))
+    t = _CONST.get(key)
+    if t is None:
+        if len(_CONST) > 1024:
+            _CONST.clear()
+        t = torch.tensor(list(values), dtype=dtype)
+        if torch.device(device).type == "cuda":
+            t = t.pin_memory().to(device, non_blocking=True)
+        _CONST[key] = t
+    return t
+
+
 def make_offsets(values, device):
-    t = torch.tensor(list(values), dtype=torch.int32, device=device)
-    return register_offsets(t, values)
+    return register_offsets(const_tensor(values, torch.int32, device), values)
 
 
 def _sizes(off):
@@ -111,18 +129,23 @@ class SectorizedFurthestSampling(Function):
             seg_first.append(len(quotas))
             quotas += q
         nseg = len(quotas)
-        new_sector_offset = torch.tensor(quotas, dtype=torch.int64).cumsum(0).to(torch.int32).to(dev, non_blocking=True)
+        acc_q, run = [], 0
+        for q in quotas:
+            run += q
+            acc_q.append(run)
+        new_sector_offset = const_tensor(acc_q, torch.int32, dev)
 
-        cloud = torch.repeat_interleave(torch.arange(b, device=dev), torch.tensor(sizes, device=dev), output_size=n)
+        cloud = torch.repeat_interleave(torch.arange(b, device=dev), const_tensor(sizes, torch.int64, dev), output_size=n)
         angle = torch.atan2(xyz[:, 0], xyz[:, 1])
-        amin = torch.full((b,), float("inf"), device=dev).scatter_reduce_(0, cloud, angle, "amin")
-        amax = torch.full((b,), float("-inf"), device=dev).scatter_reduce_(0, cloud, angle, "amax")
+        amin = torch.full((b,), float("inf"), device=dev)
+        amax = torch.full((b,), float("-inf"), device=dev)
+        N.call("rsb_segment_minmax", b, max(sizes), angle, offset, amin, amax)
         edges = _linspace_f32(amin, amax + 1e-4, num_sectors + 1)              # [b, S+1]
         # sector s  <=>  edges[s] <= angle < edges[s+1]   (count of inner edges <= angle)
         sec = (angle[:, None] >= edges[cloud][:, 1:num_sectors]).sum(1)
-        nsec_t = torch.tensor(nsec, device=dev)
+        nsec_t = const_tensor(nsec, torch.int64, dev)
         sec = torch.where(nsec_t[cloud] > 1, sec, torch.zeros_like(sec))
-        seg_id = torch.tensor(seg_first, device=dev)[cloud] + sec
+        seg_id = const_tensor(seg_first, torch.int64, dev)[cloud] + sec
         order = torch.sort(seg_id, stable=True)[1]                             # sector-major, ascending index inside
         counts = torch.bincount(seg_id, minlength=nseg)
         sector_offset = counts.cumsum(0).to(torch.int32)

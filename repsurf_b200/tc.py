@@ -383,6 +383,62 @@ def linear(x, lin):
     return _Linear.apply(x, lin.weight, lin.bias)
 
 
+class _UmbrellaMLP(Function):
+    """Conv1d(10,10) + BN + ReLU + Conv1d(10,10) + sum over the g triangles, csrc/umbrella_mlp.cu (recomputing: the
+    only tensors in HBM are the descriptor rows and the [n, 10] result)."""
+
+    @staticmethod
+    def forward(ctx, feat, W1, b1, gamma, beta, W2, b2, coef, train):
+        n, g, cin = feat.shape
+        C = W1.shape[0]
+        W1c, W2c = W1.reshape(C, cin).contiguous(), W2.reshape(C, C).contiguous()
+        out = torch.empty(n, C, device=feat.device)
+        sc, sh, mu, inv = coef
+        N.call("rsb_umbrella_mlp_forward", n * g, g, cin, C, feat, W1c, b1, W2c, b2, sc, sh, out)
+        ctx.save_for_backward(feat, W1c, b1, W2c, sc, sh, mu, inv)
+        ctx.g, ctx.train = g, train
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        feat, W1c, b1, W2c, sc, sh, mu, inv = ctx.saved_tensors
+        n, g, cin = feat.shape
+        C = W1c.shape[0]
+        acc = torch.zeros(C * C + 3 * C + C * cin + C, dtype=torch.float64, device=feat.device)
+        acc1, acc2 = acc[:C * C + 3 * C], acc[C * C + 3 * C:]
+        N.call("rsb_umbrella_mlp_backward", n * g, g, cin, C, 1 if ctx.train else 0, feat, dOut.contiguous(), W1c, b1, W2c, sc, sh, mu, inv, acc1, acc2)
+        a = acc.float()
+        dW2, db2 = a[:C * C].view(C, C, 1), a[C * C:C * C + C]
+        dbeta, dgamma = a[C * C + C:C * C + 2 * C], a[C * C + 2 * C:C * C + 3 * C]
+        o = C * C + 3 * C
+        dW1, db1 = a[o:o + C * cin].view(C, cin, 1), a[o + C * cin:]
+        return None, dW1, db1, dgamma, dbeta, dW2, db2, None, None
+
+
+def umbrella_mlp_fused(feat, conv1, bn1, conv2):
+    """feat [n, g, 10] (no gradient) -> [n, 10]; the segmentation umbrella MLP and its 'sum' aggregation
+    (segmentation/modules/repsurface_utils.py:297-302, :322-327).  Train mode uses batch statistics and updates the
+    running buffers exactly like nn.BatchNorm1d; eval mode uses the running statistics."""
+    n, g, cin = feat.shape
+    C = conv1.weight.shape[0]
+    feat = feat.contiguous()
+    batch_stats = bn1.training or bn1.running_mean is None
+    if batch_stats:
+        st = torch.zeros(2 * C, dtype=torch.float64, device=feat.device)
+        N.call("rsb_umbrella_mlp_stats", n * g, cin, C, feat, conv1.weight.detach().reshape(C, cin).contiguous(),
+               conv1.bias.detach(), st)
+        track = bn1.training and bn1.track_running_stats and bn1.running_mean is not None
+        coef = _bn_finalize(C, n * g, st, bn1.weight.detach(), bn1.bias.detach(), bn1.eps,
+                            (bn1.momentum if bn1.momentum is not None else 0.1) if track else 0.0,
+                            bn1.running_mean if track else None, bn1.running_var if track else None, feat.device)
+        if track:
+            bn1.num_batches_tracked.add_(1)
+    else:
+        coef = _bn_eval_coef([bn1])
+    return _UmbrellaMLP.apply(feat, conv1.weight, conv1.bias, bn1.weight, bn1.bias, conv2.weight, conv2.bias, coef,
+                              batch_stats)
+
+
 def umbrella_mlp(rows, conv1, bn1, conv2):
     """Segmentation umbrella MLP Conv1d(10,10)+BN+ReLU+Conv1d(10,10) over rows [N*G, 10] on the tensor cores.
     Channels are zero-padded to 12 so that every pitch is 16-byte aligned (padding columns stay exactly zero and

@@ -144,3 +144,51 @@ def test_plain_linear_matches_fp64_torch():
     out.backward(go)
     want.backward(go.double())
     assert _rel(xa.grad, xb.grad) < 1e-5 and _rel(lin.weight.grad, lin2.weight.grad) < 1e-5 and _rel(lin.bias.grad, lin2.bias.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- fused umbrella MLP
+@pytest.mark.parametrize("n,g,train", [(5000, 9, True), (777, 8, True), (3000, 5, True), (2000, 9, False)])
+def test_umbrella_mlp_fused_matches_fp64_modules(n, g, train):
+    """csrc/umbrella_mlp.cu (Conv1d+BN+ReLU+Conv1d+sum over triangles, recomputing) against the same nn modules
+    evaluated in fp64 (segmentation/modules/repsurface_utils.py:297-302, :322-327): output, all six parameter
+    gradients and the BatchNorm running buffers."""
+    import copy
+    import torch.nn as nn
+    from repsurf_b200 import tc
+    gen = torch.Generator().manual_seed(5)
+    feat = torch.randn(n, g, 10, generator=gen).to(cuda)
+    mlps = nn.Sequential(nn.Conv1d(10, 10, 1), nn.BatchNorm1d(10), nn.ReLU(True), nn.Conv1d(10, 10, 1)).to(cuda)
+    with torch.no_grad():
+        mlps[1].weight.uniform_(0.5, 1.5)
+        mlps[1].bias.normal_(0, 0.3)
+        mlps[1].running_mean.normal_(0, 0.1)
+        mlps[1].running_var.uniform_(0.5, 2.0)
+    ref = copy.deepcopy(mlps).double()
+    mlps.train(train)
+    ref.train(train)
+    # the ReLU gradient is discontinuous at z == 0: points with a pre-activation within 1e-4 of it get a zero output
+    # gradient, so that an fp32 and an fp64 evaluation cannot disagree on a mask that matters (one flipped element
+    # moves dW1 by ~1/sqrt(rows) of its norm)
+    w = torch.randn(n, 10, generator=gen).to(cuda)
+    with torch.no_grad():
+        y = ref[0](feat.double().view(n * g, 10).t().unsqueeze(0))
+        z = nn.functional.batch_norm(y, None if train else ref[1].running_mean, None if train else ref[1].running_var,
+                                     ref[1].weight, ref[1].bias, train, 0.0, ref[1].eps).squeeze(0).t()
+        w[(z.abs().amin(1) < 1e-4).view(n, g).any(1)] = 0
+    out = tc.umbrella_mlp_fused(feat, mlps[0], mlps[1], mlps[3])
+    (out * w).sum().backward()
+    want = ref(feat.double().view(n * g, 10).t().unsqueeze(0)).squeeze(0).t().reshape(n, g, 10).sum(1)
+    (want * w.double()).sum().backward()
+    scale = want.abs().max().item()
+    assert ((out.double() - want).abs().max() / scale).item() < 1e-5
+    errs = {}
+    gmax = max(q.grad.abs().max().item() for q in ref.parameters())
+    for (name, p), (_, q) in zip(mlps.named_parameters(), ref.named_parameters()):
+        # conv1.bias has an analytically zero gradient under train-mode BatchNorm: absolute criterion there
+        den = q.grad.abs().max().item() if (name != "0.bias" or not train) else gmax
+        errs[name] = ((p.grad.double() - q.grad).abs().max() / den).item()
+    assert max(errs.values()) < 1e-4, errs
+    if train:
+        assert torch.allclose(mlps[1].running_mean.double(), ref[1].running_mean, atol=1e-5)
+        assert torch.allclose(mlps[1].running_var.double(), ref[1].running_var, rtol=1e-5, atol=1e-6)
+    assert int(mlps[1].num_batches_tracked) == int(ref[1].num_batches_tracked)
