@@ -235,6 +235,9 @@ int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, float *d
 int rsb_bn_finalize(int C, long rows, const double *stats, const float *gamma, const float *beta, float eps,
                     float momentum, float *running_mean, float *running_var, float *sc, float *sh, float *mu,
                     float *inv, cudaStream_t stream);
+/* running_mean/var (+ num_batches_tracked, int64, may be NULL) of one BatchNorm from its batch sums / sums of squares. */
+int rsb_bn_update_running(int C, long rows, const double *sum, const double *sumsq, float momentum, float *running_mean,
+                          float *running_var, long long *num_batches_tracked, cudaStream_t stream);
 int rsb_pool_forward(long G, int ns, int C, const float *Y, int ldy, const float *sc, const float *sh, float *out,
                      int *arg, cudaStream_t stream);
 int rsb_pool_backward_stats(long G, int ns, int C, const float *dOut, const int *arg, const float *Y, int ldy,

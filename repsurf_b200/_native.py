@@ -36,6 +36,7 @@ _SIGS = {
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],
     "rsb_knnquery_grid": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _l],
     "rsb_umbrella_features": [_l, _i, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_bn_update_running": [_i, _l, _p, _p, _f, _p, _p, _p],
     "rsb_segment_minmax": [_i, _l, _p, _p, _p, _p],
     "rsb_umbrella_mlp_stats": [_l, _i, _i, _p, _p, _p, _p],
     "rsb_umbrella_mlp_forward": [_l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],

@@ -51,8 +51,11 @@ __device__ __forceinline__ int pos2k(uint32_t p, int q_per_thread, int bs_ref, i
 }
 
 // PPT > 0: points in registers.  PPT == 0: streaming fallback (min-dist in P.temp, xyz re-read through L2).
-template <int PPT, bool CLUSTER>
-__global__ void __launch_bounds__(PPT == 0 ? 1024 : 512, 1) fps_kernel(FpsParams P)
+// WIDE: 1024-thread CTAs (64 registers per thread: PPT <= 12) - lets ONE CTA hold a 12k-point segment and skip the
+// cluster barrier.  Measured SLOWER than a 4-CTA cluster at 10k points (1.31 vs 0.95 us/sample: one SM's issue rate
+// bounds the 13-instruction/point scan), so no default plan selects it; reachable through RSB_FPS_PLAN="1,1024".
+template <int PPT, bool CLUSTER, bool WIDE = false>
+__global__ void __launch_bounds__((PPT == 0 || WIDE) ? 1024 : 512, 1) fps_kernel(FpsParams P)
 {
     extern __shared__ __align__(16) unsigned char fps_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -265,7 +268,12 @@ int fps_launch_ppt(const FpsParams &P, int nseg, const FpsPlan &pl, cudaStream_t
         cfg.gridDim = dim3(nseg);
         cfg.attrs = nullptr;
         cfg.numAttrs = 0;
-        RSB_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<PPT, false>, P));
+        if (pl.nt > 512) {
+            if constexpr (PPT >= 1 && PPT <= 12) RSB_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<PPT, false, true>, P));
+            else { rsb_set_error("fps: 1024-thread CTAs hold at most 12 points per thread"); return (int)cudaErrorInvalidValue; }
+        } else {
+            RSB_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<PPT, false>, P));
+        }
     }
     RSB_COUNT_LAUNCH(1);
     return 0;
@@ -280,10 +288,10 @@ int fps_launch(FpsParams P, int nseg, int n_max_pts, cudaStream_t stream)
     FpsPlan pl = fps_plan(n_max);
     if (const char *e = getenv("RSB_FPS_PLAN")) {  // tuning hook: "cs,nt"
         int cs = 0, nt = 0;
-        if (sscanf(e, "%d,%d", &cs, &nt) == 2 && cs >= 1 && cs <= 16 && nt >= 32 && nt <= 512 && nt % 32 == 0) {
+        if (sscanf(e, "%d,%d", &cs, &nt) == 2 && cs >= 1 && cs <= 16 && nt >= 32 && nt <= 1024 && nt % 32 == 0 && (nt <= 512 || cs == 1)) {
             long cap = (long)cs * nt;
             int ppt = (int)((n_max + cap - 1) / cap);
-            if (ppt <= 16) { pl.cs = cs; pl.nt = nt; pl.ppt = ppt; }
+            if (ppt <= (nt > 512 ? 12 : 16)) { pl.cs = cs; pl.nt = nt; pl.ppt = ppt; }
         }
     }
     P.cs = pl.cs;

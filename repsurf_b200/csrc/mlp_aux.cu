@@ -33,6 +33,22 @@ __global__ void bn_finalize_kernel(int C, double rows, const double *__restrict_
     }
 }
 
+// running_mean / running_var / num_batches_tracked of one BatchNorm from its batch sums (torch semantics: unbiased
+// variance for the running value) - one launch instead of the dozen tiny tensor ops of the Python formulation
+__global__ void bn_running_kernel(int C, double rows, const double *__restrict__ sum, const double *__restrict__ sumsq,
+                                  float momentum, float *running_mean, float *running_var, long long *nbt)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        const double mean = sum[c] / rows;
+        double var = sumsq[c] / rows - mean * mean;
+        if (var < 0) var = 0;
+        const double unbiased = rows > 1 ? var * rows / (rows - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+}
+
 // out[g,c] = max_s relu(sc[c]*Y[g*ns+s, c] + sh[c]); arg[g,c] = first s attaining it
 __global__ void __launch_bounds__(256) pool_fwd_kernel(long G, int ns, int C, const float *__restrict__ Y, int ldy,
                                                        const float *__restrict__ sc, const float *__restrict__ sh,
@@ -310,6 +326,18 @@ RSB_EXPORT int rsb_bn_backward_coef(int C, long rows, const double *stats, int d
     bn_bwd_coef_kernel<<<RSB_DIVUP(dual ? 2 * C : C, 128), 128, 0, stream>>>(C, (double)rows, stats, dual, sc, mu, inv, a,
                                                                             b, d, dgamma, dbeta);
     RSB_CHECK_LAUNCH("bn_bwd_coef_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+RSB_EXPORT int rsb_bn_update_running(int C, long rows, const double *sum, const double *sumsq, float momentum,
+                                     float *running_mean, float *running_var, long long *num_batches_tracked,
+                                     cudaStream_t stream)
+{
+    RSB_REQUIRE(C >= 1 && rows >= 1 && sum && sumsq && running_mean && running_var, "bad arguments");
+    bn_running_kernel<<<RSB_DIVUP(C, 128), 128, 0, stream>>>(C, (double)rows, sum, sumsq, momentum, running_mean, running_var,
+                                                             num_batches_tracked);
+    RSB_CHECK_LAUNCH("bn_running_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;
 }

@@ -225,7 +225,14 @@ class _FusedSAMLP(Function):
             gemm_rows(R, F, Gf, WpT, Y=dX, ldy=Cin, y_off=P4)
         # ---- assemble parameter gradients in the order of *params
         W_l_shape, W_f_shape = meta["W_l_shape"], meta["W_f_shape"]
-        zero = lambda n: torch.zeros(n, device=dev)
+        # biases in front of a train-mode BatchNorm have an exactly zero gradient: slices of one zero buffer
+        zbuf = torch.zeros(2 * C0 + sum(grads[("W", i + 1)].shape[0] for i in range(n_extra)), device=dev)
+        zpos = [0]
+
+        def zero(n):
+            z = zbuf[zpos[0]:zpos[0] + n]
+            zpos[0] += n
+            return z
         out = [dX, None,
                dWbd[:C0, :P].reshape(W_l_shape), zero(C0), dWbd[C0:, P4:P4 + F].reshape(W_f_shape), zero(C0),
                grads[("g", 0)][:C0], grads[("be", 0)][:C0], grads[("g", 0)][C0:], grads[("be", 0)][C0:]]
@@ -235,12 +242,13 @@ class _FusedSAMLP(Function):
         return tuple(out)
 
 
-def _update_running(bn, mean, var_unbiased):
+def _update_running(bn, R, sums, sumsq):
+    """Side effects of a train-mode nn.BatchNorm forward on its buffers, from fp64 batch sums (views into the statistics
+    vector of the GEMM epilogue): one kernel (rsb_bn_update_running)."""
     if bn.track_running_stats and bn.running_mean is not None:
         m = bn.momentum if bn.momentum is not None else 0.1
-        bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-        bn.running_var.mul_(1 - m).add_(var_unbiased, alpha=m)
-        bn.num_batches_tracked.add_(1)
+        N.call("rsb_bn_update_running", sums.shape[0], R, sums, sumsq, float(m), bn.running_mean, bn.running_var,
+               bn.num_batches_tracked)
 
 
 def sa_mlp_fused(rows, pos_channel, mod, nsample, layout=None):
@@ -262,16 +270,12 @@ def sa_mlp_fused(rows, pos_channel, mod, nsample, layout=None):
     R = rows.shape[0]
     with torch.no_grad():
         C0 = mod.mlp_l0.weight.shape[0]
-        st0 = stats[0]
-        mean0 = st0[:2 * C0] / R
-        var0 = (st0[2 * C0:] / R - mean0 * mean0).clamp_min(0) * (R / max(R - 1, 1))
-        _update_running(mod.bn_l0, mean0[:C0].float(), var0[:C0].float())
-        _update_running(mod.bn_f0, mean0[C0:].float(), var0[C0:].float())
+        st0 = stats[0]                                       # [sum l | sum f | sumsq l | sumsq f]
+        _update_running(mod.bn_l0, R, st0[:C0], st0[2 * C0:3 * C0])
+        _update_running(mod.bn_f0, R, st0[C0:2 * C0], st0[3 * C0:])
         for bn, sti in zip(mod.mlp_bns, stats[1:]):
             C = sti.shape[0] // 2
-            mean = sti[:C] / R
-            var = (sti[C:] / R - mean * mean).clamp_min(0) * (R / max(R - 1, 1))
-            _update_running(bn, mean.float(), var.float())
+            _update_running(bn, R, sti[:C], sti[C:])
     return out
 
 
@@ -371,9 +375,7 @@ def linear_bn(x, lin, bn, relu):
     out, st = _LinearBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, relu, bn.eps)
     R, C = x.shape[0], lin.weight.shape[0]
     with torch.no_grad():
-        mean = st[:C] / R
-        var = (st[C:] / R - mean * mean).clamp_min(0) * (R / max(R - 1, 1))
-        _update_running(bn, mean.float(), var.float())
+        _update_running(bn, R, st[:C], st[C:])
     return out
 
 
@@ -455,9 +457,7 @@ def umbrella_mlp(rows, conv1, bn1, conv2):
     y, st = _LinearBN.apply(x, W1, b1, g1, be1, True, bn1.eps)
     R = rows.shape[0]
     with torch.no_grad():
-        mean = st[:C] / R
-        var = (st[Cp:Cp + C] / R - mean * mean).clamp_min(0) * (R / max(R - 1, 1))
-        _update_running(bn1, mean.float(), var.float())
+        _update_running(bn1, R, st[:C], st[Cp:Cp + C])
     W2 = F.pad(conv2.weight.view(C, C), (0, Cp - C, 0, Cp - C))
     b2 = F.pad(conv2.bias, (0, Cp - C))
     return _Linear.apply(y, W2, b2)[:, :C]

@@ -64,7 +64,7 @@ def test_fps_dense_fused_xyz_and_known_answer(golden_dir):
     assert torch.equal(new_xyz.cpu(), xyz[0][idx.cpu()[0].long()][None])
 
 
-@pytest.mark.parametrize("plan", ["1,64", "1,256", "2,128", "4,256", "8,512", "16,128"])
+@pytest.mark.parametrize("plan", ["1,64", "1,256", "1,1024", "2,128", "4,256", "8,512", "16,128"])
 def test_fps_all_cluster_shapes(plan, monkeypatch):
     monkeypatch.setenv("RSB_FPS_PLAN", plan)
     xyz = _cloud(3, 2048, 77)
