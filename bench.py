@@ -265,9 +265,8 @@ def main():
     from repsurf_b200.dist import FlatGrads, broadcast_module
     params = [p for p in model.parameters()]
     broadcast_module(model)
-    # one flat gradient buffer: backward accumulates straight into it, ONE all-reduce per step (3.9 MB seg / 5.9 MB cls)
+    # gradients are packed into one flat buffer after backward: ONE all-reduce per step (3.9 MB seg / 5.9 MB cls)
     fg = FlatGrads(params)
-    flat = fg.flat
     opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4)
 
     host = make_inputs(args.workload, wl["clouds"], wl["n"], 100 + rank, pin=True)
@@ -277,7 +276,7 @@ def main():
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
     def fwd_bwd(inp):
-        flat.zero_()
+        fg.zero()
         if args.workload == "seg":
             loss = crit(model([inp[0], inp[1], inp[2]]), inp[3])
         else:

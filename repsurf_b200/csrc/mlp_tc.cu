@@ -917,7 +917,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
             float *ctab = reinterpret_cast<float *>(B + 1);
             int *itab = reinterpret_cast<int *>(ctab + 5 * (TM + NT_MAX));        // AFFINE2 wrap: U index per channel
             unsigned char *ring = reinterpret_cast<unsigned char *>(itab + (TM + NT_MAX));
-            struct Region { const float *base; long ld; int quads, last_bytes, off; };   // off: float4 index in the slab
+            struct Region { const float *base; long ld; int quads, last_bytes, off, shift; };   // off: float4 index in the slab
             Region Rg[4];
             int idxmod_g = 0, idxmod_x = 0;                        // AFFINE2 wrap: U index = (k) % ku
             auto setup = [&](const Opnd &O, int c_base, int width, Region &ra, Region &rb, int &off, int &idxmod) {
@@ -939,6 +939,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                 }
                 ra.off = off; off += KC * ra.quads;
                 rb.off = off; off += KC * rb.quads;
+                // lanes of a warp cover (row, quad) pairs: 2^shift lanes per slab row, 32 >> shift rows per pass, so a
+                // narrow slab (8 quads = 32 channels) still issues full-width cp.async instructions
+                auto lanes_per_row = [](int quads) { int sh = 0; while ((1 << sh) < quads && sh < 5) sh++; return sh; };
+                ra.shift = lanes_per_row(ra.quads);
+                rb.shift = lanes_per_row(rb.quads);
             };
             auto copy_chunk = [&](long ci, int slot) {
                 if (ci < my_chunks) {
@@ -948,11 +953,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                     for (int r = 0; r < 4; r++) {
                         const Region &R = Rg[r];
                         if (R.quads == 0) continue;
-                        for (int rr = warp; rr < KC; rr += PROD_WARPS) {
+                        const int rpp = 32 >> R.shift, qpl = 1 << R.shift;
+                        for (int rr = warp * rpp + (lane >> R.shift); rr < KC; rr += PROD_WARPS * rpp) {
                             const long row = row0 + rr;
                             const bool ok = row < P.rows;
                             const float *src = R.base + (ok ? row : 0) * R.ld;
-                            for (int q = lane; q < R.quads; q += 32) {
+                            for (int q = lane & (qpl - 1); q < R.quads; q += qpl) {
                                 const int bytes = ok ? (q == R.quads - 1 ? R.last_bytes : 16) : 0;
                                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + (uint32_t)(R.off + rr * R.quads + q) * 16), "l"(src + q * 4), "r"(bytes) : "memory");
                             }

@@ -28,8 +28,9 @@ def _worker(rank, world, port, q):
     lo, hi = shard_range(8, rank, world)
     fg.zero()
     model(clouds[lo:hi]).pow(2).mean().backward()
-    fg.allreduce_mean()
-    q.put((rank, fg.flat.clone(), torch.cat([p.data.flatten() for p in model.parameters()])))
+    flat = fg.allreduce_mean()
+    assert all(torch.equal(p.grad.flatten(), v) for p, v in zip(fg.params, flat.split([p.numel() for p in fg.params])))
+    q.put((rank, flat.clone(), torch.cat([p.data.flatten() for p in model.parameters()])))
     dist.barrier()
     dist.destroy_process_group()
 
