@@ -412,22 +412,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
             const long total = my_tiles * P.n_tiles * kc_count;
 
             // ---- issue side (runs RD chunks ahead) ----
-            long iq = 0, i_tile = blockIdx.x;
+            // row pointers advance by a constant per tile (no 64-bit multiplies in the loop); rows past the end are
+            // zero-filled (src-size 0) from the operand's base address
+            long iq = 0, i_row = (long)blockIdx.x * TM + rsub;       // i_row: this thread's first row of the tile in flight
             int i_nt = 0, i_kc = 0, i_slot = 0;
             const float *ip0[4], *ip1[4];
-            bool iok[4];
+            const long step0 = (long)gridDim.x * TM * ld0, step1 = (long)gridDim.x * TM * ld1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                ip0[j] = b0 + (i_row + 32 * j) * ld0;
+                ip1[j] = has1 ? b1 + (i_row + 32 * j) * ld1 : nullptr;
+            }
             auto issue = [&]() {
                 if (iq < total) {
-                    if (i_kc == 0 && i_nt == 0) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const long rr = i_tile * TM + rsub + 32 * j;
-                            iok[j] = rr < P.rows;
-                            const long rs = iok[j] ? rr : 0;
-                            ip0[j] = b0 + rs * ld0;
-                            ip1[j] = has1 ? b1 + rs * ld1 : nullptr;
-                        }
-                    }
                     const int kl = i_kc * KC + k4 * 4;
                     const int nv = max(0, min(4, A.K - kl));
                     const int ks = nv > 0 ? A.k0 + kl : A.k0;
@@ -435,11 +432,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                     const uint32_t slot = ring0 + (uint32_t)i_slot * SLOT_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const int bytes = iok[j] ? nv * 4 : 0;
-                        if (has0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + (uint32_t)j * PIECE_STRIDE), "l"(ip0[j] + k_u), "r"(bytes) : "memory");
-                        if (has1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + (uint32_t)(4 + j) * PIECE_STRIDE), "l"(ip1[j] + ks), "r"(bytes) : "memory");
+                        const bool ok = i_row + 32 * j < P.rows;
+                        const int bytes = ok ? nv * 4 : 0;
+                        if (has0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + (uint32_t)j * PIECE_STRIDE), "l"(ok ? ip0[j] + k_u : b0), "r"(bytes) : "memory");
+                        if (has1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + (uint32_t)(4 + j) * PIECE_STRIDE), "l"(ok ? ip1[j] + ks : b1), "r"(bytes) : "memory");
                     }
-                    if (++i_kc == kc_count) { i_kc = 0; if (++i_nt == P.n_tiles) { i_nt = 0; i_tile += gridDim.x; } }
+                    if (++i_kc == kc_count) {
+                        i_kc = 0;
+                        if (++i_nt == P.n_tiles) {
+                            i_nt = 0;
+                            i_row += (long)gridDim.x * TM;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) { ip0[j] += step0; if (has1) ip1[j] += step1; }
+                        }
+                    }
                 }
                 cp_async_commit();
                 iq++;
@@ -448,6 +454,28 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
             for (int p = 0; p < RD; p++) issue();
 
             // ---- consume side ----
+            // per-channel coefficients of this thread's quad: loaded once when the operand has a single K chunk
+            Coef4 cf;
+            auto load_coef = [&](int kl, int nv, int k) {
+                if (nv == 4 && coef_vec) {
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 a4 = A.a ? __ldg(reinterpret_cast<const float4 *>(A.a + k)) : z4;
+                    const float4 d4 = A.d ? __ldg(reinterpret_cast<const float4 *>(A.d + k)) : z4;
+                    const float4 b4 = A.b ? __ldg(reinterpret_cast<const float4 *>(A.b + k)) : z4;
+                    cf.a[0] = a4.x; cf.a[1] = a4.y; cf.a[2] = a4.z; cf.a[3] = a4.w;
+                    cf.d[0] = d4.x; cf.d[1] = d4.y; cf.d[2] = d4.z; cf.d[3] = d4.w;
+                    cf.b[0] = b4.x; cf.b[1] = b4.y; cf.b[2] = b4.z; cf.b[3] = b4.w;
+                    if (A.kind == RSB_OPND_DUAL_BN_RELU) {
+                        const float4 a24 = __ldg(reinterpret_cast<const float4 *>(A.a + A.ku + k));
+                        const float4 d24 = __ldg(reinterpret_cast<const float4 *>(A.d + A.ku + k));
+                        cf.a2[0] = a24.x; cf.a2[1] = a24.y; cf.a2[2] = a24.z; cf.a2[3] = a24.w;
+                        cf.d2[0] = d24.x; cf.d2[1] = d24.y; cf.d2[2] = d24.z; cf.d2[3] = d24.w;
+                    }
+                } else if (nv > 0) {
+                    coef_load(A, k, nv, cf);
+                }
+            };
+            if (kc_count == 1) load_coef(k4 * 4, max(0, min(4, A.K - k4 * 4)), A.k0 + k4 * 4);
             uint32_t it = 0;
             int c_slot = 0;
             for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
@@ -467,24 +495,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
                         const int kl = kc * KC + k4 * 4;
                         const int nv = max(0, min(4, A.K - kl));
                         const int k = A.k0 + kl;
-                        Coef4 cf;
-                        if (nv == 4 && coef_vec) {
-                            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float4 a4 = A.a ? __ldg(reinterpret_cast<const float4 *>(A.a + k)) : z4;
-                            const float4 d4 = A.d ? __ldg(reinterpret_cast<const float4 *>(A.d + k)) : z4;
-                            const float4 b4 = A.b ? __ldg(reinterpret_cast<const float4 *>(A.b + k)) : z4;
-                            cf.a[0] = a4.x; cf.a[1] = a4.y; cf.a[2] = a4.z; cf.a[3] = a4.w;
-                            cf.d[0] = d4.x; cf.d[1] = d4.y; cf.d[2] = d4.z; cf.d[3] = d4.w;
-                            cf.b[0] = b4.x; cf.b[1] = b4.y; cf.b[2] = b4.z; cf.b[3] = b4.w;
-                            if (A.kind == RSB_OPND_DUAL_BN_RELU) {
-                                const float4 a24 = __ldg(reinterpret_cast<const float4 *>(A.a + A.ku + k));
-                                const float4 d24 = __ldg(reinterpret_cast<const float4 *>(A.d + A.ku + k));
-                                cf.a2[0] = a24.x; cf.a2[1] = a24.y; cf.a2[2] = a24.z; cf.a2[3] = a24.w;
-                                cf.d2[0] = d24.x; cf.d2[1] = d24.y; cf.d2[2] = d24.z; cf.d2[3] = d24.w;
-                            }
-                        } else if (nv > 0) {
-                            coef_load(A, k, nv, cf);
-                        }
+                        if (kc_count > 1) load_coef(kl, nv, k);
                         const uint32_t slot = ring0 + (uint32_t)c_slot * SLOT_BYTES;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
@@ -979,8 +990,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                     itab[t0 + ct] = idxmod ? (k % idxmod) : ct;
                 }
             };
+            // lim = rows of this thread's quad that exist (ragged last chunk): the rest is staged as zeros, whatever the
+            // transform makes of a zero-filled slab row
             auto stage = [&](const Opnd &O, const Region &ra, const Region &rb, int t0, int c_base, int width,
-                             const float *slab, float *hi_base, float *lo_base) {
+                             const float *slab, float *hi_base, float *lo_base, int lim) {
                 const int k4 = warp;                                  // PROD_WARPS == KC / 4 row quads
                 const int nvalid = max(0, min(width, O.K - c_base));
                 const int nb = skip_empty ? (nvalid + 31) / 32 : (width + 31) / 32;
@@ -1005,6 +1018,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                             case RSB_OPND_DUAL_BN_RELU: v[e] = fmaxf(fmaf(u, a, d) + fmaf(w, a2, d2), 0.f); break;
                             default: v[e] = fmaf(a, u, fmaf(b, w, d)); break;
                             }
+                            if (e >= lim) v[e] = 0.f;
                         }
                     }
                     float4 hi, lo;
@@ -1042,9 +1056,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                         mbar_wait(&B->empty[s], ((it / STAGES) & 1) ^ 1);
                         unsigned char *st = smem + (size_t)s * stage_bytes;
                         const float *slab = reinterpret_cast<const float *>(ring + (size_t)cslot * P.raw_slot_bytes);
-                        stage(P.G, Rg[0], Rg[1], 0, mt * TM, TM, slab, reinterpret_cast<float *>(st), reinterpret_cast<float *>(st + a_bytes));
+                        const int lim = (int)min((long)KC, P.rows - (blockIdx.x + ci * gridDim.x) * (long)KC) - warp * 4;
+                        stage(P.G, Rg[0], Rg[1], 0, mt * TM, TM, slab, reinterpret_cast<float *>(st), reinterpret_cast<float *>(st + a_bytes), lim);
                         stage(P.X, Rg[2], Rg[3], TM, nt * NT, NT, slab, reinterpret_cast<float *>(st + 2 * a_bytes),
-                              reinterpret_cast<float *>(st + 2 * a_bytes + b_bytes));
+                              reinterpret_cast<float *>(st + 2 * a_bytes + b_bytes), lim);
                         fence_proxy_async();
                         mbar_arrive(&B->full[s]);
                         if (tid == 0) mbar_arrive(&B->full[s]);

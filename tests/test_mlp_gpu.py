@@ -74,7 +74,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("G,ns,pos_c,feat_c,mlp,conv", [(300, 32, 3, 16, [32, 32, 64], 1), (64, 64, 6, 138, [128, 128, 256], 2),
-                                                         (40, 32, 3, 266, [256, 256, 512], 1), (1000, 16, 6, 10, [64, 64, 128], 2)])
+                                                         (40, 32, 3, 266, [256, 256, 512], 1), (1000, 16, 6, 10, [64, 64, 128], 2),
+                                                         (37, 24, 3, 17, [32, 32, 64], 1)])   # ragged: rows % 32 != 0
 def test_fused_sa_mlp_matches_fp64_torch(G, ns, pos_c, feat_c, mlp, conv):
     import copy
     from repsurf_b200 import tc
