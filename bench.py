@@ -355,9 +355,21 @@ def main():
         per_row = {0: o.K, 1: o.K, 2: 2 * o.K, 3: o.K + min(o.K, o.ku), 4: o.K}[o.kind]
         return rows * per_row * 4
 
+    def most_bytes(v, alg_of):
+        """GEMM entries run at many shapes per step: report the launch shape that moves the most algorithmic bytes
+        (the one the ncu traffic capture in profiles/ holds), averaged over its launches."""
+        best = max(v["each"], key=lambda at: alg_of(at[0]))[0]
+        key = alg_of(best)
+        ts = [t for a_, t in v["each"] if alg_of(a_) == key and a_[0] == best[0]]
+        return best, float(np.mean(ts))
+
     rooflines = {}
     for name, v in per_entry.items():
         a, t_ms = biggest(v)
+        if name == "rsb_gemm_wgrad":
+            a, t_ms = most_bytes(v, lambda x: opnd_bytes(x[1], x[0]) + opnd_bytes(x[2], x[0]))
+        elif name == "rsb_gemm_rows":
+            a, t_ms = most_bytes(v, lambda x: opnd_bytes(x[2], x[0]) + x[0] * x[1] * 4)
         if name.startswith("rsb_furthestsampling"):
             if name.endswith("packed"):
                 nseg, n_max = a[0], a[1]
@@ -403,9 +415,9 @@ def main():
                                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "launch_ms": t_ms, "launch": note,
                                    "algorithmic_pairs_per_launch": pairs}
     # measured DRAM traffic per launch from the committed ncu --set full capture of the same kernels
-    # (profiles/r01_ncu_full_seg_traffic.json, produced by scripts/ncu_summary.py; seg workload shapes)
+    # (profiles/r01_ncu_full_seg_v2_traffic.json, produced by scripts/ncu_summary.py; seg workload shapes)
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_seg_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_seg_v2_traffic.json")
     if os.path.exists(tpath) and args.workload == "seg":
         traffic = json.load(open(tpath))
     fam = {"rsb_gemm_wgrad": "gemm_wgrad_kernel", "rsb_gemm_rows": "gemm_rows_kernel", "rsb_knnquery_grid": "knn_grid_kernel",
