@@ -57,12 +57,17 @@ def main():
             ip=d.get("issue_pct", 0), wp=d.get("warps_pct", 0), rg=d.get("regs", 0), s1=d.get("stall_long_sb", 0), s2=d.get("stall_barrier", 0)))
     os.makedirs("profiles", exist_ok=True)
     open(f"profiles/{tag}.md", "w").write("\n".join(lines) + "\n")
-    # per-kernel traffic of the LONGEST launch of each kernel family (what bench.py reports as roofline.traffic)
+    # per-kernel traffic of one launch per kernel family (what bench.py reports as roofline.traffic): the launch that
+    # moves the most DRAM bytes for the GEMM families (bench.py reports the shape with the most algorithmic bytes),
+    # the longest launch otherwise
     fam = {}
     for d in allk:
         name = "fps_kernel" if "fps_kernel" in d["kernel"] else "knn_grid_kernel" if "knn_grid" in d["kernel"] else \
             "gemm_wgrad_kernel" if "wgrad" in d["kernel"] else "gemm_rows_kernel" if "gemm_rows" in d["kernel"] else d["kernel"]
-        if name not in fam or d.get("time", 0) > fam[name]["ms"]:
+        gemm = name.startswith("gemm_")
+        key = (lambda e: e["dram_bytes"]) if gemm else (lambda e: e["ms"])
+        cand = {"ms": d.get("time", 0), "dram_bytes": d.get("dram_rd", 0) + d.get("dram_wr", 0)}
+        if name not in fam or key(cand) > key(fam[name]):
             fam[name] = {"ms": d.get("time", 0), "dram_bytes": d.get("dram_rd", 0) + d.get("dram_wr", 0), "l2_bytes": d.get("l2_bytes", 0)}
     json.dump(fam, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
     print("\n".join(lines))
