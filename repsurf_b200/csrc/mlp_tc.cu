@@ -158,11 +158,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+// round-to-nearest (ties away) to tf32, as cvt.rna.tf32.f32 does for every finite input: add half a tf32 ulp to the
+// magnitude, clear the 13 low mantissa bits.  The PTX instruction compiles to the same two integer operations PLUS
+// an |x| < inf test and a select per value (8 conversions per staged float4: a fifth of the split's instructions);
+// the guard only matters for NaN payloads, which never enter a GEMM here (check_nan_umb repairs the descriptors).
 __device__ __forceinline__ float to_tf32(float x)
 {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // ---- operand transform ------------------------------------------------------------------------------------

@@ -122,7 +122,11 @@ class _FusedSAMLP(Function):
         bias0 = torch.cat([b_l, b_f]).detach()
         Wp0, _, _ = prep_weight(Wbd)
         Y0 = torch.empty(R, 2 * C0, device=dev)
-        st = torch.zeros(4 * C0, dtype=torch.float64, device=dev)
+        # batch statistics of every layer: slices of ONE zeroed fp64 buffer (one fill launch per block)
+        widths = [4 * C0] + [2 * params[8 + 4 * i].shape[0] for i in range(n_extra)]
+        stbuf = torch.zeros(sum(widths), dtype=torch.float64, device=dev)
+        stats_of = list(torch.split(stbuf, widths))
+        st = stats_of[0]
         gemm_rows(R, 2 * C0, opnd(OPND_RAW, X, Cin), Wp0, Y=Y0, bias=bias0, stats=st)
         coefs = [_bn_finalize(2 * C0, R, st, torch.cat([g_l, g_f]).detach(), torch.cat([be_l, be_f]).detach(), eps, 0.0,
                               None, None, dev)]
@@ -137,7 +141,7 @@ class _FusedSAMLP(Function):
             W2 = W.reshape(Ci, -1).detach().contiguous()
             Wp, _, _ = prep_weight(W2)
             Yi = torch.empty(R, Ci, device=dev)
-            sti = torch.zeros(2 * Ci, dtype=torch.float64, device=dev)
+            sti = stats_of[i + 1]
             gemm_rows(R, Ci, prev, Wp, Y=Yi, bias=b.detach(), stats=sti)
             co = _bn_finalize(Ci, R, sti, g.detach(), be.detach(), eps, 0.0, None, None, dev)
             coefs.append(co)
@@ -167,8 +171,14 @@ class _FusedSAMLP(Function):
         CL = Ys[L].shape[1]
         sc, sh, mu, inv = coefs[L]
         grads = {}
+        # zeroed accumulators of the whole backward: slices of one fp64 buffer (BatchNorm-backward statistics) and of
+        # one fp32 buffer (weight gradients) - two fill launches per block instead of two per layer
+        st_w = [2 * CL] + [(3 if l - 1 == 0 else 2) * Ws[l - 1].shape[1] for l in range(L, 0, -1)]
+        st_parts = list(torch.split(torch.zeros(sum(st_w), dtype=torch.float64, device=dev), st_w))
+        dw_n = [Ws[l - 1].numel() for l in range(L, 0, -1)] + [2 * C0 * Cin]
+        dw_parts = list(torch.split(torch.zeros(sum(dw_n), device=dev), dw_n))
         # ---- max-pool backward -> BatchNorm-backward coefficients of the last layer
-        st = torch.zeros(2 * CL, dtype=torch.float64, device=dev)
+        st = st_parts.pop(0)
         dm = torch.empty(G, CL, device=dev)
         N.call("rsb_pool_backward_stats", G, ns, CL, dOut.contiguous(), arg, Ys[L], Ys[L].stride(0), sc, sh, mu, inv, dm, st)
         co = torch.empty(5, CL, device=dev)
@@ -190,14 +200,14 @@ class _FusedSAMLP(Function):
                 Aprev = opnd(OPND_DUAL, Ys[0], C0, a=coefs[0][0], d=coefs[0][1], ku=C0)
             else:
                 Aprev = opnd(OPND_BN_RELU, Ys[l - 1], Cp, a=coefs[l - 1][0], d=coefs[l - 1][1])
-            dW = torch.zeros(Cl, Cp, device=dev)
+            dW = dw_parts.pop(0).view(Cl, Cp)
             gemm_wgrad(R, Gop, Aprev, dW)
             grads[("W", l)] = dW
             # dgrad through W_l, ReLU mask + BatchNorm-backward statistics of layer l-1
             WpT, _, _ = prep_weight(W, transposed=True)      # operand [N=C_{l-1}, K=C_l]
             dual = (l - 1 == 0)
             dZ = torch.empty(R, Cp, device=dev)
-            stp = torch.zeros((3 if dual else 2) * Cp, dtype=torch.float64, device=dev)
+            stp = st_parts.pop(0)
             scp, shp, mup, invp = coefs[l - 1]
             if Cp % 4 == 0:
                 # plain tensor-core dgrad, then one bandwidth-bound pass: ReLU mask + BatchNorm-backward statistics
@@ -213,7 +223,7 @@ class _FusedSAMLP(Function):
             Gop = opnd(OPND_AFFINE2, dZ, width, a=cop[0], b=cop[1], d=cop[2], V=Ys[l - 1], ku=Cp)
             dZ0, cop0 = dZ, cop
         # ---- first layer: weight gradient of the block-diagonal GEMM, input gradient of the feature columns
-        dWbd = torch.zeros(2 * C0, Cin, device=dev)
+        dWbd = dw_parts.pop(0).view(2 * C0, Cin)
         gemm_wgrad(R, Gop, opnd(OPND_RAW, X, Cin), dWbd)
         dX = None
         P4, F = meta["feat_col"], meta["feat_channels"]
