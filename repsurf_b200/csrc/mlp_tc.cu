@@ -284,36 +284,9 @@ __device__ __forceinline__ void opnd_eval4(const Opnd &O, const OpndFlags &F, co
     opnd_apply4(O, c, u, w, k, nv, g, sidx, v);
 }
 
-// 16-byte asynchronous global->shared copy; bytes beyond src_bytes are zero-filled (src_bytes may be 0)
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(rsb_smem_addr(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// one channel k of row r (wgrad staging walks 4 consecutive rows of a fixed channel)
-__device__ __forceinline__ float opnd_eval1(const Opnd &O, long r, int k, float a, float b, float d, float a2, float d2,
-                                            long g, int sidx)
-{
-    switch (O.kind) {
-    case RSB_OPND_RAW:
-        return __ldg(O.U + (size_t)r * O.ldu + k);
-    case RSB_OPND_BN_RELU:
-        return fmaxf(fmaf(__ldg(O.U + (size_t)r * O.ldu + k), a, d), 0.f);
-    case RSB_OPND_DUAL_BN_RELU: {
-        const float *u = O.U + (size_t)r * O.ldu;
-        return fmaxf(fmaf(__ldg(u + k), a, d) + fmaf(__ldg(u + O.ku + k), a2, d2), 0.f);
-    }
-    case RSB_OPND_AFFINE2:
-        return fmaf(a, __ldg(O.U + (size_t)r * O.ldu + (k % O.ku)), fmaf(b, __ldg(O.V + (size_t)r * O.ldv + k), d));
-    default: {
-        const float dz = (__ldg(O.arg + (size_t)g * O.ldu + k) == sidx) ? __ldg(O.U + (size_t)g * O.ldu + k) : 0.f;
-        return fmaf(a, dz, fmaf(b, __ldg(O.V + (size_t)r * O.ldv + k), d));
-    }
-    }
-}
 
 __device__ __forceinline__ void split4(const float *v, float4 &hi, float4 &lo)
 {

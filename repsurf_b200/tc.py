@@ -449,25 +449,3 @@ def umbrella_mlp_fused(feat, conv1, bn1, conv2):
         coef = _bn_eval_coef([bn1])
     return _UmbrellaMLP.apply(feat, conv1.weight, conv1.bias, bn1.weight, bn1.bias, conv2.weight, conv2.bias, coef,
                               batch_stats)
-
-
-def umbrella_mlp(rows, conv1, bn1, conv2):
-    """Segmentation umbrella MLP Conv1d(10,10)+BN+ReLU+Conv1d(10,10) over rows [N*G, 10] on the tensor cores.
-    Channels are zero-padded to 12 so that every pitch is 16-byte aligned (padding columns stay exactly zero and
-    are sliced off); gradients reach the real parameters through the padding ops."""
-    import torch.nn.functional as F
-    C = conv1.weight.shape[0]
-    Cin = rows.shape[1]
-    Cp, Kp = (C + 3) // 4 * 4, (Cin + 3) // 4 * 4
-    x = F.pad(rows, (0, Kp - Cin)) if Kp != Cin else rows
-    W1 = F.pad(conv1.weight.view(C, Cin), (0, Kp - Cin, 0, Cp - C))
-    b1 = F.pad(conv1.bias, (0, Cp - C))
-    g1 = F.pad(bn1.weight, (0, Cp - C), value=1.0)
-    be1 = F.pad(bn1.bias, (0, Cp - C))
-    y, st = _LinearBN.apply(x, W1, b1, g1, be1, True, bn1.eps)
-    R = rows.shape[0]
-    with torch.no_grad():
-        _update_running(bn1, R, st[:C], st[Cp:Cp + C])
-    W2 = F.pad(conv2.weight.view(C, C), (0, Cp - C, 0, Cp - C))
-    b2 = F.pad(conv2.bias, (0, Cp - C))
-    return _Linear.apply(y, W2, b2)[:, :C]
