@@ -367,7 +367,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
             // Everything that does not change per chunk (shared-memory offsets, row pointers, validity) is hoisted:
             // the per-chunk work is address adds, the transform itself and the hi/lo split.
             const int RD = P.raw_depth;
-            const int k4 = tid & 7, rsub = tid >> 3;                                   // rows rsub + 32*j
+            // thread -> (channel quad k4, rows rsub + 32*j).  The 8 lanes of a quarter-warp take the 8 rows of ONE core
+            // matrix (same k4), so a warp-wide 128-bit tile store covers whole 128-byte core matrices: conflict-free.
+            // (With k4 = tid & 7 the 8 lanes hit the same 4 banks, 128 B apart: ncu counted 37 M store bank conflicts in
+            // 45 M store wavefronts and the LSU data pipe at 65-73 % of peak - the limiter of this kernel.)
+            const int k4 = (tid >> 3) & 7, rsub = (tid >> 6) * 8 + (tid & 7);
             constexpr uint32_t PIECE_STRIDE = PROD_THREADS * 16;                       // bytes between (piece, j) planes
             constexpr uint32_t SLOT_BYTES = 2 * 4 * PIECE_STRIDE;
             const uint32_t ring0 = rsb_smem_addr(stat_tile + 4 * 32 * 33) + (uint32_t)tid * 16;
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_rows_kernel(const __grid_cons
         // ===== producers: two groups of 4 warps take alternate chunks, so two stages are being loaded at any time.
         // Inside a group: thread = (channel quad k4, row sub-index), 8 rows per thread per chunk, coefficients hoisted.
         const int grp = warp >> 2, gt = tid & (GROUP_THREADS - 1);
-        const int k4 = gt & 7, rsub = gt >> 3;            // rsub 0..15 -> rows rsub + 16*j
+        const int k4 = (gt >> 3) & 7, rsub = (gt >> 6) * 8 + (gt & 7);   // rows rsub + 16*j; quarter-warp = one core matrix
         const OpndFlags F = opnd_flags(A);
         uint32_t it = 0;
         for (long tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
