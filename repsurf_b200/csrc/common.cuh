@@ -49,6 +49,15 @@ int rsb_sm_count();
 // ---- exact squared distance (rule R1) -------------------------------------------------------
 // nvcc contracts the reference's `dx*dx + dy*dy + dz*dz` into FMUL(y) / FFMA(x) / FFMA(z)
 // (SURVEY.md §8(c)); spelled with intrinsics so no optimisation level can change the rounding.
+// i / d for 0 <= i, d > 0: the flat element index of the gather / elementwise kernels is a 64-bit `long`, whose
+// division is a ~60-instruction software routine; whenever the dividend fits 32 bits (every launch at the workloads'
+// sizes except the largest row matrices) the 32-bit hardware path gives the same quotient.
+__device__ __forceinline__ long rsb_div(long i, long d)
+{
+    if (((unsigned long)i | (unsigned long)d) >> 32) return i / d;
+    return (long)((unsigned)i / (unsigned)d);
+}
+
 __device__ __forceinline__ float rsb_sqdist(float ax, float ay, float az, float bx, float by, float bz)
 {
     const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(TPB) dense_gather_fwd(int b, int c, int n, lon
 {
     const long total = (long)b * per;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long bi = i / per, j = i - bi * per;
+        const long bi = rsb_div(i, per), j = i - bi * per;
         const int a = __ldg(idx + i);
         const T *src = f + (size_t)bi * c * n + a;
         T *dst = out + (size_t)bi * c * per + j;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(TPB) dense_gather_bwd(int b, int c, int n, lon
 {
     const long total = (long)b * per;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long bi = i / per, j = i - bi * per;
+        const long bi = rsb_div(i, per), j = i - bi * per;
         const int a = __ldg(idx + i);
         float *dst = gf + (size_t)bi * c * n + a;
         const float *src = go + (size_t)bi * c * per + j;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(TPB) dense_interp_fwd(int b, int c, int m, int
 {
     const long total = (long)b * n;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long bi = i / n, p = i - bi * n;
+        const long bi = rsb_div(i, n), p = i - bi * n;
         const int i0 = idx[i * 3], i1 = idx[i * 3 + 1], i2 = idx[i * 3 + 2];
         const float w0 = w[i * 3], w1 = w[i * 3 + 1], w2 = w[i * 3 + 2];
         const float *src = f + (size_t)bi * c * m;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TPB) dense_interp_bwd(int b, int c, int n, int
 {
     const long total = (long)b * n;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long bi = i / n, p = i - bi * n;
+        const long bi = rsb_div(i, n), p = i - bi * n;
         const int i0 = idx[i * 3], i1 = idx[i * 3 + 1], i2 = idx[i * 3 + 2];
         const float w0 = w[i * 3], w1 = w[i * 3 + 1], w2 = w[i * 3 + 2];
         float *dst = gf + (size_t)bi * c * m;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(TPB) packed_group_fwd(long rows, int c, const 
     const int cv = c / VEC;
     const long total = rows * cv;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long r = i / cv;
+        const long r = rsb_div(i, cv);
         const int ch = (int)(i - r * cv);
         const int a = __ldg(idx + r);
         if (VEC == 4) {
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(TPB) packed_group_bwd(long rows, int c, const 
 {
     const long total = rows * c;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long r = i / c;
+        const long r = rsb_div(i, c);
         const int ch = (int)(i - r * c);
         atomicAdd(gi + (size_t)__ldg(idx + r) * c + ch, __ldg(go + i));
     }
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(TPB) packed_interp_fwd(long n, int c, int k, c
 {
     const long total = n * c;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long p = i / c;
+        const long p = rsb_div(i, c);
         const int ch = (int)(i - p * c);
         float acc = out[i];
         for (int j = 0; j < k; j++)
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(TPB) packed_interp_bwd(long n, int c, int k, c
 {
     const long total = n * c;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long p = i / c;
+        const long p = rsb_div(i, c);
         const int ch = (int)(i - p * c);
         const float g = __ldg(go + i);
         for (int j = 0; j < k; j++)
@@ -171,14 +171,14 @@ __global__ void __launch_bounds__(TPB) group_rows_fwd(long rows, int ns, int pol
 {
     const long total = rows * ld;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long r = i / ld;
+        const long r = rsb_div(i, ld);
         const int c = (int)(i - r * ld);
         const int src = __ldg(idx + r);
         float v = 0.f;
         if (c < P4) {
             const int P = polar ? 6 : 3;
             if (c < P) {
-                const float *q = new_xyz + (r / ns) * 3;
+                const float *q = new_xyz + rsb_div(r, ns) * 3;
                 const float dx = __ldg(xyz + (size_t)src * 3) - __ldg(q), dy = __ldg(xyz + (size_t)src * 3 + 1) - __ldg(q + 1),
                             dz = __ldg(xyz + (size_t)src * 3 + 2) - __ldg(q + 2);
                 if (c == 0) v = dx;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TPB) group_rows_bwd(long rows, int P4, int Cn,
     const int C = Cn + Cf;
     const long total = rows * C;
     for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
-        const long r = i / C;
+        const long r = rsb_div(i, C);
         const int c = (int)(i - r * C);
         const float g = __ldg(drows + (size_t)r * ld + P4 + c);
         const int src = __ldg(idx + r);

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(long G, int ns, int C, co
 {
     const long total = G * C;
     for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-        const long g = i / C;
+        const long g = rsb_div(i, C);
         const int c = (int)(i - g * C);
         const float a = __ldg(sc + c), b = __ldg(sh + c);
         const float *y = Y + (size_t)g * ns * ldy + c;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(long rows, int C, const f
     const int quads = C / 4;
     const long total = rows * quads;
     for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-        const long r = i / quads;
+        const long r = rsb_div(i, quads);
         const int c = (int)(i - r * quads) * 4;
         const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + (size_t)r * ldy + c));
         const float4 a = __ldg(reinterpret_cast<const float4 *>(sc + c)), b = __ldg(reinterpret_cast<const float4 *>(sh + c));
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) pool_bn_bwd_dense_kernel(long G, int ns, 
     const int quads = C / 4;
     const long total = G * quads;
     for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-        const long g = i / quads;
+        const long g = rsb_div(i, quads);
         const int c = (int)(i - g * quads) * 4;
         const float4 a4 = __ldg(reinterpret_cast<const float4 *>(a + c)), b4 = __ldg(reinterpret_cast<const float4 *>(b + c));
         const float4 d4 = __ldg(reinterpret_cast<const float4 *>(d + c));

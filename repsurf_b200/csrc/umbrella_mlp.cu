@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(UTPB) umb_backward1_kernel(long rows, int g, c
     for (long r = blockIdx.x * (long)UTPB + threadIdx.x; r < rows; r += (long)gridDim.x * UTPB) {
         float x[UC], dO[UC], xh[UC], h[UC], dZ[UC];
         load_row(X, r, x);
-        load_row(dOut, r / g, dO);
+        load_row(dOut, rsb_div(r, g), dO);
         backward_row(S, x, dO, xh, h, dZ);
 #pragma unroll
         for (int c = 0; c < UC; c++) {
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(UTPB) umb_backward2_kernel(long rows, int g, i
     for (long r = blockIdx.x * (long)UTPB + threadIdx.x; r < rows; r += (long)gridDim.x * UTPB) {
         float x[UC], dO[UC], xh[UC], h[UC], dZ[UC];
         load_row(X, r, x);
-        load_row(dOut, r / g, dO);
+        load_row(dOut, rsb_div(r, g), dO);
         backward_row(S, x, dO, xh, h, dZ);
 #pragma unroll
         for (int k = 0; k < UC; k++) {
