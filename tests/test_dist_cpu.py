@@ -65,3 +65,31 @@ def test_shard_range_partitions_all_clouds():
         got = [shard_range(64, r, world) for r in range(world)]
         assert got[0][0] == 0 and got[-1][1] == 64
         assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+
+
+def test_flat_grads_single_process_pack_roundtrip():
+    """One process: nothing is reduced; a forced pack must leave every .grad unchanged and mirror it in `flat`."""
+    from repsurf_b200.dist import FlatGrads
+    torch.manual_seed(3)
+    model = nn.Sequential(nn.Linear(5, 7), nn.ReLU(), nn.Linear(7, 2), nn.Linear(2, 2))
+    fg = FlatGrads(model.parameters())
+    fg.zero()
+    model[:3](torch.randn(11, 5)).sum().backward()          # the last layer is unused: its gradients stay None
+    before = [None if p.grad is None else p.grad.clone() for p in fg.params]
+    assert fg.allreduce_mean() is None                       # world size 1: no packing at all
+    flat = fg.allreduce_mean(force_pack=True)
+    o = 0
+    for p, b in zip(fg.params, before):
+        want = torch.zeros_like(p) if b is None else b
+        assert torch.equal(p.grad, want) and torch.equal(flat[o:o + p.numel()].view_as(p), want)
+        o += p.numel()
+
+
+def test_const_tensor_is_cached_by_value():
+    from repsurf_b200.seg import pointops as P
+    a = P.const_tensor([3, 5, 9], torch.int32, "cpu")
+    b = P.const_tensor((3, 5, 9), torch.int32, "cpu")
+    c = P.const_tensor([3, 5, 9], torch.int64, "cpu")
+    assert a is b and a is not c and a.tolist() == [3, 5, 9] and c.dtype == torch.int64
+    off = P.make_offsets([4, 10], "cpu")
+    assert P.host_offsets(off) == (4, 10) and P.make_offsets([4, 10], "cpu") is off
