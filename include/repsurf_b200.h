@@ -220,6 +220,10 @@ typedef struct {
     int kind, dual;
 } rsb_epi_t;
 
+/* Kernel generation of rsb_gemm_rows / rsb_gemm_wgrad: 0 (default) = the TMA-fed kernels (csrc/mlp_tc2.cu) whenever
+ * every stored tensor of the operands is 16-byte aligned with a row pitch that is a multiple of 4 floats, else the
+ * first-generation cp.async kernels (csrc/mlp_tc.cu); 1 = always the first generation (A/B comparisons, tests). */
+void rsb_tc_set_generation(int gen);
 /* Y = A @ W^T with W pre-split by rsb_linear_tc_prep_weight(N, A->K, ...). */
 int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float *Wp, const rsb_epi_t *E, cudaStream_t stream);
 /* dW[m, n] += sum_r G(r, m) * X(r, n);  dW is [G->K, ldw] fp32, accumulated with atomics (caller zeroes it). */

@@ -1177,7 +1177,10 @@ __global__ void weight_prep_kernel(const float *__restrict__ W, int N, int K, in
 }
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-inline int pick_nt(int N) { return N <= NT_MAX ? round_up(N, 16) : NT_MAX; }
+// N tile width: the fewest tiles of <= 256 columns, balanced (N = 272 -> 160 + 112, not 256 + 16) and, when there are
+// several, a multiple of 32 so that the 32-column store boxes of one tile never reach into the next; the same rule
+// lays out the pre-split weights (weight_prep_kernel) and is applied by both kernel generations
+inline int pick_nt(int N) { const int t = (N + NT_MAX - 1) / NT_MAX; return round_up((N + t - 1) / t, t > 1 ? 32 : 16); }
 
 int check_opnd(const Opnd &O, const char *what)
 {
@@ -1218,6 +1221,10 @@ RSB_EXPORT int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float 
     if (check_opnd(*A, "rsb_gemm_rows")) return (int)cudaErrorInvalidValue;
     RSB_REQUIRE(E->kind == RSB_EPI_BIAS_STATS || (E->Yl && E->sc && E->sh && E->mu && E->inv), "dgrad epilogue needs Yl/sc/sh/mu/inv");
     if (rows == 0) return 0;
+    {   // TMA-fed kernel (mlp_tc2.cu) whenever the operands meet its alignment rules
+        const int r2 = rsb_gemm_rows2_launch(rows, N, A, Wp, E, stream);
+        if (r2 >= 0) return r2;
+    }
     RowsParams P;
     P.A = *A; P.E = *E; P.Wp = Wp; P.rows = rows; P.N = N;
     P.NT = pick_nt(N);
@@ -1259,6 +1266,10 @@ RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *
     RSB_REQUIRE(rows >= 0 && G && X && dW, "bad arguments");
     if (check_opnd(*G, "rsb_gemm_wgrad(G)") || check_opnd(*X, "rsb_gemm_wgrad(X)")) return (int)cudaErrorInvalidValue;
     if (rows == 0) return 0;
+    {
+        const int r2 = rsb_gemm_wgrad2_launch(rows, G, X, dW, ldw, stream);
+        if (r2 >= 0) return r2;
+    }
     WgradParams P;
     P.G = *G; P.X = *X; P.dW = dW; P.ldw = ldw; P.rows = rows;
     P.M = G->K; P.N = X->K;

@@ -1,0 +1,874 @@
+// mlp_tc2.cu — TMA-fed versions of the shared-MLP GEMMs (same contract as mlp_tc.cu's rsb_gemm_rows / rsb_gemm_wgrad,
+// which dispatch here whenever the operands satisfy TMA's 16-byte alignment rules).
+//
+// Why a second generation: the first-generation kernels staged every operand element through SIMT code three times
+// (cp.async issue into a private ring, ring -> registers -> canonical tile, per-element transposition for wgrad); ncu's
+// source view (profiles/r01_ncu_source_gemm.md) showed 500-700 SASS instructions per warp and chunk, issue slots 27-45 %
+// busy, DRAM 14-30 %: a dependent-issue chain, not a bandwidth or tensor kernel.  Here
+//   * one elected thread moves the RAW operand tiles with TMA (cp.async.bulk.tensor.2d) straight into the swizzled
+//     layout the tensor core reads: K-major SWIZZLE_128B tiles for Y = A W^T, MN-major 32-byte-atom tiles for
+//     dW = G^T X — the transposition of the weight-gradient operands is done by the MMA's major-ness bit, not by code;
+//   * 16 transform warps rewrite those tiles IN PLACE: one LDS.128 (two for two-tensor operands), the BatchNorm /
+//     ReLU / BatchNorm-backward transform, the hi/lo tf32 split, two STS.128 — ~40 instructions per 16-byte piece,
+//     conflict-free because a warp touches 512 contiguous bytes.  Two-tensor operands (dual first layer, BatchNorm
+//     backward) need no extra buffer: "hi" replaces the first raw tile, "lo" the second;
+//   * weights small enough (<= 64 KB pre-split) stay resident in shared memory for the whole kernel;
+//   * the epilogue leaves through a swizzled staging tile and TMA stores (clipped at the ragged edge by the tensor
+//     map), column statistics are read back from the same tile and accumulated in fp64 in shared memory;
+//   * the input-gradient GEMM applies the ReLU mask of the layer below and accumulates that layer's BatchNorm-backward
+//     statistics in its epilogue (no separate streaming pass over dZ);
+//   * the weight-gradient grid is (M tile) x (N tile) x (row split): every CTA owns one dW tile and flushes it once
+//     with vector reductions, instead of every CTA cycling through all tiles.
+// Numerics are unchanged: 3xTF32 (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM).
+#include "tc_common.cuh"
+#include "mlp_tc.h"
+#include <stdlib.h>
+
+using namespace rsbtc;
+
+namespace {
+
+typedef rsb_opnd_t Opnd;
+typedef rsb_epi_t Epi;
+
+constexpr int TM = 128;                 // UMMA M
+constexpr int KC = 32;                  // reduction depth of a pipeline stage (4 k-steps of 8 tf32)
+constexpr int A_TILE = TM * KC * 4;     // 16 KB: one 128 x 32 fp32 tile
+constexpr int BOX = 32 * 32 * 4;        // 4 KB: one 32-row x 32-channel box of a weight-gradient operand
+constexpr int XF_WARPS = 16;            // transform warps
+constexpr int XF_THREADS = XF_WARPS * 32;
+constexpr int LOAD_WARP = XF_WARPS;     // TMA issuer
+constexpr int MMA_WARP = XF_WARPS + 1;  // tcgen05.mma issuer (also owns the TMEM allocation)
+constexpr int EPI_WARP0 = XF_WARPS + 2; // 4 epilogue warps
+constexpr int THREADS2 = (XF_WARPS + 2 + 4) * 32;
+constexpr int STAGES_MAX = 4;
+constexpr int SMEM_MAX = 227 * 1024;
+
+// ---- host: tensor maps ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encoder()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// [rows, cols] fp32 view with row pitch ld (floats); cols beyond the extent and rows beyond `rows` read as zero
+int make_map(CUtensorMap *m, const float *base, long cols, long rows, long ld, int box_cols, int box_rows, CUtensorMapSwizzle sw)
+{
+    EncodeTiledFn fn = encoder();
+    if (!fn) { rsb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return 1; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rsb_set_error("cuTensorMapEncodeTiled failed (%d): base %p cols %ld rows %ld ld %ld box %dx%d", (int)r, (const void *)base, cols, rows, ld,
+                      box_cols, box_rows);
+        return 1;
+    }
+    return 0;
+}
+
+inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- device: operand transform -------------------------------------------------------------------------------
+struct Coef {
+    float4 a, d, b, a2, d2;
+};
+
+__device__ __forceinline__ float4 ld_coef4(const float *p, int k, int nv)
+{
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!p || nv <= 0) return r;
+    if (nv == 4 && (((uintptr_t)(p + k)) & 15) == 0) return __ldg(reinterpret_cast<const float4 *>(p + k));
+    r.x = __ldg(p + k);
+    if (nv > 1) r.y = __ldg(p + k + 1);
+    if (nv > 2) r.z = __ldg(p + k + 2);
+    if (nv > 3) r.w = __ldg(p + k + 3);
+    return r;
+}
+
+// coefficients of channels k .. k+3 (k includes k0); channels past the operand's width get zeros, which makes every
+// transform return 0 there (the raw values are zero-filled by TMA)
+__device__ __forceinline__ void load_coef(const Opnd &O, int k, int nv, Coef &c)
+{
+    c.a = ld_coef4(O.a, k, nv);
+    c.d = ld_coef4(O.d, k, nv);
+    c.b = ld_coef4(O.b, k, nv);
+    if (O.kind == RSB_OPND_DUAL_BN_RELU) {
+        c.a2 = ld_coef4(O.a, O.ku + k, nv);
+        c.d2 = ld_coef4(O.d, O.ku + k, nv);
+    } else {
+        c.a2 = c.d2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__device__ __forceinline__ float4 xform(int kind, const float4 u, const float4 w, const Coef &c)
+{
+    float4 v;
+    switch (kind) {
+    case RSB_OPND_RAW:
+        v = u;
+        break;
+    case RSB_OPND_BN_RELU:
+        v.x = relu_nan(fmaf(u.x, c.a.x, c.d.x)); v.y = relu_nan(fmaf(u.y, c.a.y, c.d.y));
+        v.z = relu_nan(fmaf(u.z, c.a.z, c.d.z)); v.w = relu_nan(fmaf(u.w, c.a.w, c.d.w));
+        break;
+    case RSB_OPND_DUAL_BN_RELU:
+        v.x = relu_nan(fmaf(u.x, c.a.x, c.d.x) + fmaf(w.x, c.a2.x, c.d2.x));
+        v.y = relu_nan(fmaf(u.y, c.a.y, c.d.y) + fmaf(w.y, c.a2.y, c.d2.y));
+        v.z = relu_nan(fmaf(u.z, c.a.z, c.d.z) + fmaf(w.z, c.a2.z, c.d2.z));
+        v.w = relu_nan(fmaf(u.w, c.a.w, c.d.w) + fmaf(w.w, c.a2.w, c.d2.w));
+        break;
+    default:   // RSB_OPND_AFFINE2
+        v.x = fmaf(c.a.x, u.x, fmaf(c.b.x, w.x, c.d.x)); v.y = fmaf(c.a.y, u.y, fmaf(c.b.y, w.y, c.d.y));
+        v.z = fmaf(c.a.z, u.z, fmaf(c.b.z, w.z, c.d.z)); v.w = fmaf(c.a.w, u.w, fmaf(c.b.w, w.w, c.d.w));
+        break;
+    }
+    return v;
+}
+
+struct alignas(16) Bars2 {
+    uint64_t raw_full[STAGES_MAX], full[STAGES_MAX], empty[STAGES_MAX], acc_full[2], acc_empty[2], w_bar;
+    uint32_t tmem_slot, pad;
+};
+
+template <int COLS>
+__device__ __forceinline__ uint32_t cta_setup(Bars2 *B, int tid, int warp, int full_count)
+{
+    if (tid == 0) {
+        for (int s = 0; s < STAGES_MAX; s++) { mbar_init(&B->raw_full[s], 1); mbar_init(&B->full[s], full_count); mbar_init(&B->empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&B->acc_full[a], 1); mbar_init(&B->acc_empty[a], 128); }
+        mbar_init(&B->w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rsb_smem_addr(&B->tmem_slot)), "n"(COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return B->tmem_slot;
+}
+
+template <int COLS>
+__device__ __forceinline__ void cta_teardown(uint32_t tmem_base, int warp)
+{
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(COLS));
+    }
+}
+
+// ============================================================================================================
+// Y = A @ W^T  (forward and input gradient)
+// ============================================================================================================
+struct Rows2Params {
+    CUtensorMap mapA0, mapA1, mapY;
+    Opnd A;
+    Epi E;
+    const float *Wp;
+    long rows;
+    int N, NT, n_tiles, k_chunks, stages;
+    int n_pieces;     // raw tensors behind the operand (1: RAW / BN_RELU, 2: DUAL / AFFINE2)
+    int w_resident;   // the pre-split weights of all (N tile, K chunk) pairs stay in shared memory
+    int v_bufs;       // staging tiles per epilogue warp for the outgoing block (1 or 2)
+    int n_tab;        // per-column epilogue tables in shared memory (bias | sc, sh, mu [, second half])
+    int smem_stats;   // statistics accumulate in fp64 in shared memory (single N tile), else per-tile atomics
+    int has_y;
+};
+
+__global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_constant__ Rows2Params P)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw0 = rsb_smem_addr(smem_raw);
+    const uint32_t base = (raw0 + 1023u) & ~1023u;
+    unsigned char *gbase = smem_raw + (base - raw0);
+
+    const int NT = P.NT, S = P.stages, KCH = P.k_chunks;
+    const uint32_t w_chunk_bytes = 2u * (uint32_t)NT * KC * 4;
+    const uint32_t stage_bytes = 2 * A_TILE + (P.w_resident ? 0u : w_chunk_bytes);
+    const uint32_t w_res = base + (uint32_t)S * stage_bytes;
+    const uint32_t w_res_bytes = P.w_resident ? (uint32_t)(P.n_tiles * KCH) * w_chunk_bytes : 0u;
+    const bool mask = P.E.kind == RSB_EPI_RELU_MASK;
+    const int n_stat = mask ? (P.E.dual ? 3 : 2) : 2;
+    const int epi_tiles = P.v_bufs + (mask ? (P.E.dual ? 2 : 1) : 0);
+    const uint32_t epi0 = w_res + w_res_bytes;
+    const int Npad = P.n_tiles * NT;
+    float *tabs = reinterpret_cast<float *>(gbase + (epi0 - base) + 4u * epi_tiles * 4096u);
+    double *sacc = reinterpret_cast<double *>(tabs + (size_t)P.n_tab * Npad);
+    Bars2 *B = reinterpret_cast<Bars2 *>(reinterpret_cast<unsigned char *>(sacc) + (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0));
+
+    const Opnd &A = P.A;
+    const Epi &E = P.E;
+
+    // ---- one-time shared-memory state ----
+    // epilogue tables, zero-padded to the tile grid
+    for (int i = tid; i < P.n_tab * Npad; i += THREADS2) {
+        const int t = i / Npad, n = i - t * Npad;
+        float v = 0.f;
+        if (n < P.N) {
+            if (!mask) v = E.bias ? __ldg(E.bias + n) : 0.f;
+            else {
+                const int half = t / 3, which = t - half * 3;          // [sc sh mu | sc2 sh2 mu2]
+                const float *src = which == 0 ? E.sc : (which == 1 ? E.sh : E.mu);
+                v = __ldg(src + half * P.N + n);
+            }
+        }
+        tabs[i] = v;
+    }
+    if (P.smem_stats)
+        for (int i = tid; i < 4 * n_stat * NT; i += THREADS2) sacc[i] = 0.0;
+    // single-tensor operands: the "lo" tile is written by the transform only where channels exist; clear it once
+    if (P.n_pieces == 1)
+        for (int s = 0; s < S; s++)
+            for (int i = tid; i < A_TILE / 16; i += THREADS2) sts128(base + (uint32_t)s * stage_bytes + A_TILE + (uint32_t)i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+    fence_proxy_async();
+    if (warp == LOAD_WARP && lane == 0) {
+        prefetch_tmap(&P.mapA0);
+        if (P.n_pieces == 2) prefetch_tmap(&P.mapA1);
+        if (P.has_y) prefetch_tmap(&P.mapY);
+    }
+    const uint32_t tmem_base = cta_setup<512>(B, tid, warp, XF_THREADS + (P.w_resident ? 0 : 1));
+
+    const long n_row_tiles = (P.rows + TM - 1) / TM;
+    const long n_work = n_row_tiles * P.n_tiles;
+
+    if (warp < XF_WARPS) {
+        // =============================== transform warps ===============================
+        // thread -> the 16-byte pieces tid and tid + 512 of the 128 x 32 tile (rows tid/8 and tid/8 + 64): both share
+        // (row & 7) and the physical chunk, hence the logical channel quad and its coefficients
+        const int q = (tid & 7) ^ ((tid >> 3) & 7);
+        Coef cf;
+        const bool hoist = KCH == 1;
+        int nv = max(0, min(4, A.K - q * 4));
+        if (hoist) load_coef(A, A.k0 + q * 4, nv, cf);
+        const bool two = P.n_pieces == 2;
+        const bool zero_lo = !two && KCH > 1;       // stale "lo" data of a full chunk under an invalid quad of the last chunk
+        uint32_t it = 0;
+        for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+            for (int kc = 0; kc < KCH; kc++, it++) {
+                const int s = it % S;
+                if (!hoist) {
+                    nv = max(0, min(4, A.K - (kc * KC + q * 4)));
+                    load_coef(A, A.k0 + kc * KC + q * 4, nv, cf);
+                }
+                mbar_wait(&B->raw_full[s], (it / S) & 1);
+                const uint32_t a0 = base + (uint32_t)s * stage_bytes + (uint32_t)tid * 16;
+                if (nv > 0) {
+                    float4 u[2], x[2];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        u[j] = lds128(a0 + j * (XF_THREADS * 16));
+                        x[j] = two ? lds128(a0 + A_TILE + j * (XF_THREADS * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        float4 hi, lo;
+                        split4(xform(A.kind, u[j], x[j], cf), hi, lo);
+                        sts128(a0 + j * (XF_THREADS * 16), hi);
+                        sts128(a0 + A_TILE + j * (XF_THREADS * 16), lo);
+                    }
+                } else if (zero_lo) {
+                    sts128(a0 + A_TILE, make_float4(0.f, 0.f, 0.f, 0.f));
+                    sts128(a0 + A_TILE + XF_THREADS * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+                fence_proxy_async();
+                mbar_arrive(&B->full[s]);
+            }
+        }
+    } else if (warp == LOAD_WARP) {
+        // =============================== TMA issuer ===============================
+        if (lane == 0) {
+            if (P.w_resident) {
+                mbar_arrive_expect_tx(&B->w_bar, w_res_bytes);
+                bulk_g2s(w_res, P.Wp, w_res_bytes, &B->w_bar);
+            }
+            uint32_t it = 0;
+            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const long tile = w / P.n_tiles;
+                const int nt = (int)(w - tile * P.n_tiles);
+                const int row0 = (int)(tile * TM);
+                for (int kc = 0; kc < KCH; kc++, it++) {
+                    const int s = it % S;
+                    mbar_wait(&B->empty[s], ((it / S) & 1) ^ 1);
+                    const uint32_t st = base + (uint32_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&B->raw_full[s], (uint32_t)P.n_pieces * A_TILE);
+                    tma_load_2d(st, &P.mapA0, kc * KC, row0, &B->raw_full[s]);
+                    if (P.n_pieces == 2) tma_load_2d(st + A_TILE, &P.mapA1, kc * KC, row0, &B->raw_full[s]);
+                    if (!P.w_resident) {
+                        mbar_arrive_expect_tx(&B->full[s], w_chunk_bytes);
+                        bulk_g2s(st + 2 * A_TILE, P.Wp + ((size_t)nt * KCH + kc) * (2 * (size_t)NT * KC), w_chunk_bytes, &B->full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // =============================== MMA issuer ===============================
+        const uint32_t idesc = umma_idesc_tf32(TM, NT, false);
+        if (P.w_resident) mbar_wait(&B->w_bar, 0);
+        uint32_t it = 0, acc_it = 0;
+        for (long w = blockIdx.x; w < n_work; w += gridDim.x, acc_it++) {
+            const int nt = (int)(w % P.n_tiles);
+            const int ab = acc_it & 1;
+            mbar_wait(&B->acc_empty[ab], ((acc_it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(ab * 256);
+            for (int kc = 0; kc < KCH; kc++, it++) {
+                const int s = it % S;
+                mbar_wait(&B->full[s], (it / S) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = base + (uint32_t)s * stage_bytes;
+                    const uint32_t a_hi = st, a_lo = st + A_TILE;
+                    const uint32_t b_hi = P.w_resident ? w_res + (uint32_t)(nt * KCH + kc) * w_chunk_bytes : st + 2 * A_TILE;
+                    const uint32_t b_lo = b_hi + (uint32_t)NT * KC * 4;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ks++) {
+                        // A: K-major SWIZZLE_128B (8 tf32 = 32 B inside the 128-byte row); W: canonical no-swizzle K-major
+                        // tiles written by weight_prep_kernel (core matrices 128 B apart along K, 1024 B along N)
+                        const uint64_t dah = umma_desc(a_hi + ks * 32, 16, 1024, 2), dal = umma_desc(a_lo + ks * 32, 16, 1024, 2);
+                        const uint64_t dbh = umma_desc(b_hi + ks * 256, 128, 1024, 0), dbl = umma_desc(b_lo + ks * 256, 128, 1024, 0);
+                        umma_tf32(tmem_d, dal, dbh, idesc, (kc | ks) ? 1u : 0u);   // small terms first
+                        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&B->empty[s]);
+                    if (kc == KCH - 1) umma_commit(&B->acc_full[ab]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =============================== epilogue ===============================
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int ew = warp - EPI_WARP0;        // staging / accumulator slot
+        const uint32_t my_epi = epi0 + (uint32_t)ew * epi_tiles * 4096u;
+        const uint32_t p_tile = my_epi + (uint32_t)P.v_bufs * 4096u;   // mask epilogue: v*(yl-mu) tile(s)
+        double *my_acc = sacc + (size_t)ew * n_stat * NT;
+        const float *t_bias = tabs, *t_sc = tabs, *t_sh = tabs + Npad, *t_mu = tabs + 2 * Npad;
+        const uint32_t my_row_off = (uint32_t)lane * 128u;             // this lane's row inside a staging tile
+        const int sw = lane & 7;
+        uint32_t acc_it = 0, vb = 0;
+        for (long w = blockIdx.x; w < n_work; w += gridDim.x, acc_it++) {
+            const long tile = w / P.n_tiles;
+            const int nt = (int)(w - tile * P.n_tiles);
+            const int ab = acc_it & 1;
+            const long row = tile * TM + q * 32 + lane;
+            const bool row_ok = row < P.rows;
+            mbar_wait(&B->acc_full[ab], (acc_it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
+            const int ncols = min(NT, P.N - nt * NT);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                const int nl = nt * NT + c0;                       // first column of the block (table index == column)
+                // the staging tile of this block must have been read by its previous TMA store
+                if (P.has_y) {
+                    if (lane == 0) { if (P.v_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+                    __syncwarp();
+                }
+                const uint32_t vt = my_epi + (vb % (uint32_t)P.v_bufs) * 4096u + my_row_off;
+                if (!mask) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(t_bias + nl + 4 * c);
+                        float4 o;
+                        o.x = row_ok ? v[4 * c] + b4.x : 0.f; o.y = row_ok ? v[4 * c + 1] + b4.y : 0.f;
+                        o.z = row_ok ? v[4 * c + 2] + b4.z : 0.f; o.w = row_ok ? v[4 * c + 3] + b4.w : 0.f;
+                        sts128(vt + (uint32_t)((c ^ sw) << 4), o);
+                    }
+                } else {
+                    // dgrad: ReLU mask of the layer below recomputed from its stored pre-BatchNorm output, and the
+                    // products the BatchNorm-backward statistics need
+                    const float *yl = E.Yl + (size_t)(row_ok ? row : 0) * E.ldl + nl;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const bool ok = row_ok && nl + 4 * c < P.N;
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 y = ok ? __ldg(reinterpret_cast<const float4 *>(yl + 4 * c)) : z4;
+                        const float4 sc = *reinterpret_cast<const float4 *>(t_sc + nl + 4 * c);
+                        const float4 sh = *reinterpret_cast<const float4 *>(t_sh + nl + 4 * c);
+                        const float4 mu = *reinterpret_cast<const float4 *>(t_mu + nl + 4 * c);
+                        float4 z;
+                        z.x = fmaf(y.x, sc.x, sh.x); z.y = fmaf(y.y, sc.y, sh.y); z.z = fmaf(y.z, sc.z, sh.z); z.w = fmaf(y.w, sc.w, sh.w);
+                        float4 y2 = z4, mu2 = z4;
+                        if (E.dual) {
+                            y2 = ok ? __ldg(reinterpret_cast<const float4 *>(yl + P.N + 4 * c)) : z4;
+                            const float4 sc2 = *reinterpret_cast<const float4 *>(t_sc + 3 * Npad + nl + 4 * c);
+                            const float4 sh2 = *reinterpret_cast<const float4 *>(t_sh + 3 * Npad + nl + 4 * c);
+                            mu2 = *reinterpret_cast<const float4 *>(t_mu + 3 * Npad + nl + 4 * c);
+                            z.x += fmaf(y2.x, sc2.x, sh2.x); z.y += fmaf(y2.y, sc2.y, sh2.y);
+                            z.z += fmaf(y2.z, sc2.z, sh2.z); z.w += fmaf(y2.w, sc2.w, sh2.w);
+                        }
+                        float4 o;
+                        o.x = (ok && z.x > 0.f) ? v[4 * c] : 0.f; o.y = (ok && z.y > 0.f) ? v[4 * c + 1] : 0.f;
+                        o.z = (ok && z.z > 0.f) ? v[4 * c + 2] : 0.f; o.w = (ok && z.w > 0.f) ? v[4 * c + 3] : 0.f;
+                        sts128(vt + (uint32_t)((c ^ sw) << 4), o);
+                        sts128(p_tile + my_row_off + (uint32_t)((c ^ sw) << 4),
+                               make_float4(o.x * (y.x - mu.x), o.y * (y.y - mu.y), o.z * (y.z - mu.z), o.w * (y.w - mu.w)));
+                        if (E.dual)
+                            sts128(p_tile + 4096u + my_row_off + (uint32_t)((c ^ sw) << 4),
+                                   make_float4(o.x * (y2.x - mu2.x), o.y * (y2.y - mu2.y), o.z * (y2.z - mu2.z), o.w * (y2.w - mu2.w)));
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (P.has_y && lane == 0) {
+                    tma_store_2d(&P.mapY, nl, (int)(tile * TM + q * 32), vt - my_row_off);
+                    bulk_commit();
+                }
+                if (E.stats) {
+                    // column `lane` of the block: sums over the warp's 32 rows, read back from the staging tile(s)
+                    const uint32_t cbase = (vt - my_row_off) + (uint32_t)((lane & 3) << 2);
+                    const int cq = lane >> 2;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+                    if (!mask) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            float t;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(cbase + (uint32_t)i * 128u + (uint32_t)((cq ^ (i & 7)) << 4)));
+                            s0 += t;
+                            s1 = fmaf(t, t, s1);
+                        }
+                    } else {
+                        const uint32_t pbase = p_tile + (uint32_t)((lane & 3) << 2);
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const uint32_t off = (uint32_t)i * 128u + (uint32_t)((cq ^ (i & 7)) << 4);
+                            float t, p1;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(cbase + off));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p1) : "r"(pbase + off));
+                            s0 += t;
+                            s1 += p1;
+                            if (E.dual) {
+                                float p2;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p2) : "r"(pbase + 4096u + off));
+                                s2 += p2;
+                            }
+                        }
+                    }
+                    const int n = nl + lane;
+                    if (P.smem_stats) {
+                        if (c0 + lane < NT) {               // NT is a multiple of 16, not of 32
+                            double *a = my_acc + c0 + lane;
+                            a[0] += (double)s0;
+                            a[NT] += (double)s1;
+                            if (n_stat == 3) a[2 * NT] += (double)s2;
+                        }
+                    } else if (n < P.N) {
+                        atomicAdd(E.stats + n, (double)s0);
+                        if (!mask) atomicAdd(E.stats + P.N + n, (double)s1);
+                        else {
+                            atomicAdd(E.stats + P.N + n, (double)s1 * (double)__ldg(E.inv + n));
+                            if (E.dual) atomicAdd(E.stats + 2 * P.N + n, (double)s2 * (double)__ldg(E.inv + P.N + n));
+                        }
+                    }
+                    __syncwarp();      // the product tile is reused by the next block
+                }
+                vb++;
+            }
+            tc_fence_before();
+            mbar_arrive(&B->acc_empty[ab]);
+        }
+        if (P.smem_stats && E.stats) {
+            __syncwarp();
+            for (int c = lane; c < NT; c += 32) {
+                if (c >= P.N) break;
+                const double s0 = my_acc[c], s1 = my_acc[NT + c];
+                if (s0 != 0.0 || s1 != 0.0) {
+                    atomicAdd(E.stats + c, s0);
+                    atomicAdd(E.stats + P.N + c, mask ? s1 * (double)__ldg(E.inv + c) : s1);
+                }
+                if (n_stat == 3) {
+                    const double s2 = my_acc[2 * NT + c];
+                    if (s2 != 0.0) atomicAdd(E.stats + 2 * P.N + c, s2 * (double)__ldg(E.inv + P.N + c));
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    cta_teardown<512>(tmem_base, warp);
+}
+
+// ============================================================================================================
+// dW[m, n] += sum_r G(r, m) * X(r, n)   (weight gradient; reduction over rows)
+// ============================================================================================================
+struct Wgrad2Params {
+    CUtensorMap mapG0, mapG1, mapX0, mapX1;
+    Opnd G, X;
+    float *dW;
+    int ldw;
+    long rows;
+    int M, N, NT, NTB, m_tiles, n_tiles, splits, stages;
+    int g_pieces, x_pieces;
+};
+
+// first column (in the piece's tensor map) of the 32-channel box that starts at logical channel c of operand O
+__device__ __forceinline__ int piece0_col(const Opnd &O, int c) { return O.kind == RSB_OPND_AFFINE2 ? (O.k0 + c) % O.ku : O.k0 + c; }
+
+__global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_constant__ Wgrad2Params P)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw0 = rsb_smem_addr(smem_raw);
+    const uint32_t base = (raw0 + 1023u) & ~1023u;
+    unsigned char *gbase = smem_raw + (base - raw0);
+
+    const int NT = P.NT, NTB = P.NTB, S = P.stages;
+    const uint32_t x_bytes = (uint32_t)NTB * BOX;                   // one of raw/hi, raw/lo of the X tile
+    const uint32_t stage_bytes = 2 * A_TILE + 2 * x_bytes;
+    constexpr int TABW = TM + 256;
+    float *ctab = reinterpret_cast<float *>(gbase + (size_t)S * stage_bytes);   // [a | b | d | a2 | d2] x (G 128 | X 256)
+    Bars2 *B = reinterpret_cast<Bars2 *>(ctab + 5 * TABW);
+
+    const int sp = blockIdx.x % P.splits;
+    const int tile_id = blockIdx.x / P.splits;
+    const int nt = tile_id % P.n_tiles, mt = tile_id / P.n_tiles;
+    const int vg = min(TM, P.M - mt * TM), vx = min(NT, P.N - nt * NT);       // valid channels of the two tiles
+    const int gb = (vg + 31) / 32, xb = (vx + 31) / 32;                       // boxes that are loaded and transformed
+    const long n_chunks = (P.rows + KC - 1) / KC;
+    const long cps = (n_chunks + P.splits - 1) / P.splits;
+    const long c_begin = (long)sp * cps, c_end = min(n_chunks, c_begin + cps);
+    const long my_chunks = max(0L, c_end - c_begin);
+
+    // coefficient tables of the two channel tiles (zeros past the valid channels)
+    for (int i = tid; i < 5 * TABW; i += THREADS2) {
+        const int t = i / TABW, c = i - t * TABW;
+        const bool isg = c < TM;
+        const Opnd &O = isg ? P.G : P.X;
+        const int cl = isg ? c : c - TM;
+        const int ch = (isg ? mt * TM : nt * NT) + cl;
+        float v = 0.f;
+        if (cl < (isg ? vg : vx)) {
+            const int k = O.k0 + ch;
+            if (t == 0) v = O.a ? __ldg(O.a + k) : 0.f;
+            else if (t == 1) v = O.b ? __ldg(O.b + k) : 0.f;
+            else if (t == 2) v = O.d ? __ldg(O.d + k) : 0.f;
+            else if (O.kind == RSB_OPND_DUAL_BN_RELU) v = __ldg((t == 3 ? O.a : O.d) + O.ku + k);
+        }
+        ctab[i] = v;
+    }
+    // boxes that are never loaded (channels past the matrices) still feed the MMA: their products land in accumulator
+    // rows / columns nobody reads, but keep them finite
+    for (int i = tid; i < S * (int)(stage_bytes / 16); i += THREADS2) sts128(base + (uint32_t)i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+    fence_proxy_async();
+    if (warp == LOAD_WARP && lane == 0) {
+        prefetch_tmap(&P.mapG0); prefetch_tmap(&P.mapX0);
+        if (P.g_pieces == 2) prefetch_tmap(&P.mapG1);
+        if (P.x_pieces == 2) prefetch_tmap(&P.mapX1);
+    }
+    const uint32_t tmem_base = cta_setup<256>(B, tid, warp, XF_THREADS);
+
+    if (my_chunks > 0) {
+        if (warp < XF_WARPS) {
+            // =============================== transform warps ===============================
+            // 16-byte piece p of a region: box p >> 8, k-row (p >> 3) & 31, physical chunk p & 7; with 32-byte swizzle atoms
+            // the logical channel quad is chunk ^ ((row & 3) << 1).  A thread's pieces tid + 512 j share row and quad.
+            const int kr = (tid >> 3) & 31;
+            const int q = (tid & 7) ^ ((kr & 3) << 1);
+            const int box0 = tid >> 8;                                   // boxes box0, box0 + 2, ...
+            const bool g2 = P.g_pieces == 2, x2 = P.x_pieces == 2;
+            uint32_t it = 0;
+            for (long ci = 0; ci < my_chunks; ci++, it++) {
+                const int s = it % S;
+                const int lim = (int)min((long)KC, P.rows - (c_begin + ci) * KC);   // valid rows of this chunk
+                const bool row_ok = kr < lim;
+                mbar_wait(&B->raw_full[s], (it / S) & 1);
+                const uint32_t st = base + (uint32_t)s * stage_bytes;
+                // ---- G tile ----
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int bx = box0 + 2 * j;
+                    if (bx >= gb) break;
+                    const uint32_t addr = st + (uint32_t)(tid + XF_THREADS * j) * 16;
+                    const int ch = bx * 32 + q * 4;
+                    Coef c;
+                    c.a = *reinterpret_cast<const float4 *>(ctab + ch);
+                    c.b = *reinterpret_cast<const float4 *>(ctab + TABW + ch);
+                    c.d = *reinterpret_cast<const float4 *>(ctab + 2 * TABW + ch);
+                    c.a2 = *reinterpret_cast<const float4 *>(ctab + 3 * TABW + ch);
+                    c.d2 = *reinterpret_cast<const float4 *>(ctab + 4 * TABW + ch);
+                    const float4 u = lds128(addr);
+                    const float4 x = g2 ? lds128(addr + A_TILE) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = xform(P.G.kind, u, x, c);
+                    if (!row_ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 hi, lo;
+                    split4(v, hi, lo);
+                    sts128(addr, hi);
+                    sts128(addr + A_TILE, lo);
+                }
+                // ---- X tile ----
+                for (int bx = box0; bx < xb; bx += 2) {
+                    const uint32_t addr = st + 2 * A_TILE + (uint32_t)(bx * 256 + (tid & 255)) * 16;
+                    const int ch = TM + bx * 32 + q * 4;
+                    Coef c;
+                    c.a = *reinterpret_cast<const float4 *>(ctab + ch);
+                    c.b = *reinterpret_cast<const float4 *>(ctab + TABW + ch);
+                    c.d = *reinterpret_cast<const float4 *>(ctab + 2 * TABW + ch);
+                    c.a2 = *reinterpret_cast<const float4 *>(ctab + 3 * TABW + ch);
+                    c.d2 = *reinterpret_cast<const float4 *>(ctab + 4 * TABW + ch);
+                    const float4 u = lds128(addr);
+                    const float4 x = x2 ? lds128(addr + x_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = xform(P.X.kind, u, x, c);
+                    if (!row_ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 hi, lo;
+                    split4(v, hi, lo);
+                    sts128(addr, hi);
+                    sts128(addr + x_bytes, lo);
+                }
+                fence_proxy_async();
+                mbar_arrive(&B->full[s]);
+            }
+        } else if (warp == LOAD_WARP) {
+            // =============================== TMA issuer ===============================
+            if (lane == 0) {
+                const uint32_t tx = (uint32_t)(P.g_pieces * gb + P.x_pieces * xb) * BOX;
+                uint32_t it = 0;
+                for (long ci = 0; ci < my_chunks; ci++, it++) {
+                    const int s = it % S;
+                    mbar_wait(&B->empty[s], ((it / S) & 1) ^ 1);
+                    const uint32_t st = base + (uint32_t)s * stage_bytes;
+                    const int row0 = (int)((c_begin + ci) * KC);
+                    mbar_arrive_expect_tx(&B->raw_full[s], tx);
+                    for (int g = 0; g < gb; g++) {
+                        const int c = mt * TM + g * 32;
+                        tma_load_2d(st + (uint32_t)g * BOX, &P.mapG0, piece0_col(P.G, c), row0, &B->raw_full[s]);
+                        if (P.g_pieces == 2) tma_load_2d(st + A_TILE + (uint32_t)g * BOX, &P.mapG1, P.G.k0 + c, row0, &B->raw_full[s]);
+                    }
+                    for (int x = 0; x < xb; x++) {
+                        const int c = nt * NT + x * 32;
+                        tma_load_2d(st + 2 * A_TILE + (uint32_t)x * BOX, &P.mapX0, piece0_col(P.X, c), row0, &B->raw_full[s]);
+                        if (P.x_pieces == 2) tma_load_2d(st + 2 * A_TILE + x_bytes + (uint32_t)x * BOX, &P.mapX1, P.X.k0 + c, row0, &B->raw_full[s]);
+                    }
+                }
+            }
+        } else if (warp == MMA_WARP) {
+            // =============================== MMA issuer ===============================
+            const uint32_t idesc = umma_idesc_tf32(TM, NT, true);
+            uint32_t it = 0;
+            for (long ci = 0; ci < my_chunks; ci++, it++) {
+                const int s = it % S;
+                mbar_wait(&B->full[s], (it / S) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = base + (uint32_t)s * stage_bytes;
+                    const uint32_t a_hi = st, a_lo = st + A_TILE, b_hi = st + 2 * A_TILE, b_lo = b_hi + x_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ks++) {
+                        // MN-major, 32-byte swizzle atoms: 32-channel groups BOX bytes apart (LBO), 4-row groups 512 B apart
+                        // (SBO), 8 reduction rows = 1024 B per k-step
+                        const uint32_t adv = ks * 1024;
+                        const uint64_t dah = umma_desc(a_hi + adv, BOX, 512, 1), dal = umma_desc(a_lo + adv, BOX, 512, 1);
+                        const uint64_t dbh = umma_desc(b_hi + adv, BOX, 512, 1), dbl = umma_desc(b_lo + adv, BOX, 512, 1);
+                        umma_tf32(tmem_base, dal, dbh, idesc, (ci | ks) ? 1u : 0u);
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&B->empty[s]);
+                    if (ci == my_chunks - 1) umma_commit(&B->acc_full[0]);
+                }
+                __syncwarp();
+            }
+        } else {
+            // =============================== epilogue: flush the dW tile ===============================
+            const int q = warp & 3;
+            mbar_wait(&B->acc_full[0], 0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int ml = q * 32 + lane;                          // channel of G inside the tile
+            const bool vec = (P.ldw & 3) == 0 && (((uintptr_t)P.dW) & 15) == 0 && ((nt * NT) & 3) == 0;
+            for (int c0 = 0; c0 < vx; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                if (ml < vg) {
+                    float *dst = P.dW + (size_t)(mt * TM + ml) * P.ldw + nt * NT + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (vec && c0 + j + 4 <= vx) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                                if (c0 + j + e < vx) atomicAdd(dst + j + e, v[j + e]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    cta_teardown<256>(tmem_base, warp);
+}
+
+int g_force_v1 = [] { const char *v = getenv("RSB_TC_V1"); return (v && v[0] && v[0] != '0') ? 1 : 0; }();
+
+bool opnd_tma_ok(const Opnd &O)
+{
+    if (O.kind == RSB_OPND_POOLED) return false;
+    if (!al16(O.U) || (O.ldu & 3) || (O.k0 & 3)) return false;
+    if (O.kind == RSB_OPND_DUAL_BN_RELU && (O.ku & 3)) return false;
+    if (O.kind == RSB_OPND_AFFINE2 && (!al16(O.V) || (O.ldv & 3) || (O.ku & 3))) return false;
+    return true;
+}
+
+}  // namespace
+
+RSB_EXPORT void rsb_tc_set_generation(int gen) { g_force_v1 = gen == 1 ? 1 : 0; }
+
+// Returns 0 when the launch was made, -1 when the problem is not eligible (the caller then uses the first-generation
+// kernel), > 0 on errors.
+int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp, const rsb_epi_t *E, cudaStream_t stream)
+{
+    if (g_force_v1 || !encoder()) return -1;
+    if (!opnd_tma_ok(*A)) return -1;
+    if (rows + TM >= (1L << 31)) return -1;
+    if (A->kind == RSB_OPND_AFFINE2 && (A->k0 % A->ku) + A->K > A->ku) return -1;     // U would wrap inside the operand
+    const bool mask = E->kind == RSB_EPI_RELU_MASK;
+    if (E->Y && (!al16(E->Y) || (E->ldy & 3))) return -1;
+    if (mask && (!al16(E->Yl) || (E->ldl & 3) || (N & 3))) return -1;
+    // same tiling rule as pick_nt() in mlp_tc.cu, which laid out the pre-split weight buffer
+    const int nt0 = (N + 255) / 256;
+    const int NT = round_up((N + nt0 - 1) / nt0, nt0 > 1 ? 32 : 16);
+    const int n_tiles = (N + NT - 1) / NT;
+
+    Rows2Params P;
+    memset(&P, 0, sizeof(P));
+    P.A = *A; P.E = *E; P.Wp = Wp; P.rows = rows; P.N = N; P.NT = NT; P.n_tiles = n_tiles;
+    P.k_chunks = (A->K + KC - 1) / KC;
+    P.n_pieces = (A->kind == RSB_OPND_DUAL_BN_RELU || A->kind == RSB_OPND_AFFINE2) ? 2 : 1;
+    P.has_y = E->Y != nullptr;
+    P.n_tab = mask ? (E->dual ? 6 : 3) : 1;
+    P.smem_stats = (E->stats && n_tiles == 1) ? 1 : 0;
+    const int n_stat = mask ? (E->dual ? 3 : 2) : 2;
+    const size_t w_chunk = 2 * (size_t)NT * KC * 4;
+    const size_t w_total = (size_t)n_tiles * P.k_chunks * w_chunk;
+    const int Npad = n_tiles * NT;
+    bool fit = false;
+    for (int vb = 2; vb >= 1 && !fit; vb--) {
+        const int epi_tiles = vb + (mask ? (E->dual ? 2 : 1) : 0);
+        const size_t fixed = 4 * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 + (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0) +
+                             sizeof(Bars2) + 1024 + 64;
+        if (fixed + 2 * (2 * (size_t)A_TILE) > (size_t)SMEM_MAX) continue;
+        const size_t budget = SMEM_MAX - fixed;
+        for (int res = 1; res >= 0 && !fit; res--) {
+            if (res && w_total > 64 * 1024) continue;
+            const size_t stage_b = 2 * (size_t)A_TILE + (res ? 0 : w_chunk);
+            if (budget < (res ? w_total : 0) + 2 * stage_b) continue;
+            int st = (int)((budget - (res ? w_total : 0)) / stage_b);
+            if (st > STAGES_MAX) st = STAGES_MAX;
+            if (res && st < 3) continue;           // residency must not starve the pipeline
+            P.stages = st; P.w_resident = res; P.v_bufs = vb;
+            fit = true;
+        }
+    }
+    if (!fit) return -1;
+    const int epi_tiles = P.v_bufs + (mask ? (E->dual ? 2 : 1) : 0);
+    const size_t stage_b = 2 * (size_t)A_TILE + (P.w_resident ? 0 : w_chunk);
+    const size_t smem = (size_t)P.stages * stage_b + (P.w_resident ? w_total : 0) + 4 * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 +
+                        (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0) + sizeof(Bars2) + 1024 + 64;
+
+    // operand pieces: columns [0, K) of the map are the operand's channels k0 .. k0 + K
+    const float *p0 = A->kind == RSB_OPND_AFFINE2 ? A->U + (A->k0 % A->ku) : A->U + A->k0;
+    if (make_map(&P.mapA0, p0, A->K, rows, A->ldu, KC, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return (int)cudaErrorInvalidValue;
+    if (P.n_pieces == 2) {
+        const float *p1 = A->kind == RSB_OPND_DUAL_BN_RELU ? A->U + A->ku + A->k0 : A->V + A->k0;
+        const long ld1 = A->kind == RSB_OPND_DUAL_BN_RELU ? A->ldu : A->ldv;
+        if (make_map(&P.mapA1, p1, A->K, rows, ld1, KC, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return (int)cudaErrorInvalidValue;
+    }
+    if (P.has_y && make_map(&P.mapY, E->Y, N, rows, E->ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return (int)cudaErrorInvalidValue;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        RSB_CUDA(cudaFuncSetAttribute(gemm_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        attr_set = true;
+    }
+    const long n_work = ((rows + TM - 1) / TM) * n_tiles;
+    const int grid = (int)(n_work < rsb_sm_count() ? n_work : rsb_sm_count());
+    gemm_rows2_kernel<<<grid, THREADS2, smem, stream>>>(P);
+    RSB_CHECK_LAUNCH("gemm_rows2_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+int rsb_gemm_wgrad2_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, float *dW, int ldw, cudaStream_t stream)
+{
+    if (g_force_v1 || !encoder()) return -1;
+    if (!opnd_tma_ok(*G) || !opnd_tma_ok(*X)) return -1;
+    if (rows + KC >= (1L << 31)) return -1;
+    // AFFINE2 operands whose U tensor wraps (k % ku) inside the operand: every 32-channel box must stay inside one period
+    auto wrap_ok = [](const Opnd &O) {
+        if (O.kind != RSB_OPND_AFFINE2) return true;
+        if ((O.k0 % O.ku) + O.K <= O.ku) return true;
+        return (O.ku % 32) == 0 && (O.k0 % 32) == 0;
+    };
+    if (!wrap_ok(*G) || !wrap_ok(*X)) return -1;
+
+    Wgrad2Params P;
+    memset(&P, 0, sizeof(P));
+    P.G = *G; P.X = *X; P.dW = dW; P.ldw = ldw; P.rows = rows;
+    P.M = G->K; P.N = X->K;
+    P.m_tiles = (P.M + TM - 1) / TM;
+    P.n_tiles = (P.N + 255) / 256;
+    P.NT = round_up((P.N + P.n_tiles - 1) / P.n_tiles, 16);
+    // N tiles start at multiples of NT: with more than one tile they must also be multiples of the 32-channel boxes
+    if (P.n_tiles > 1 && (P.NT % 32)) P.NT = round_up(P.NT, 32);
+    if (P.NT > 256) return -1;
+    P.n_tiles = (P.N + P.NT - 1) / P.NT;
+    P.NTB = (P.NT + 31) / 32;
+    P.g_pieces = (G->kind == RSB_OPND_DUAL_BN_RELU || G->kind == RSB_OPND_AFFINE2) ? 2 : 1;
+    P.x_pieces = (X->kind == RSB_OPND_DUAL_BN_RELU || X->kind == RSB_OPND_AFFINE2) ? 2 : 1;
+    const size_t stage_b = 2 * (size_t)A_TILE + 2 * (size_t)P.NTB * BOX;
+    const size_t fixed = 5 * (size_t)(TM + 256) * 4 + sizeof(Bars2) + 1024 + 64;
+    int st = (int)((SMEM_MAX - fixed) / stage_b);
+    if (st > STAGES_MAX) st = STAGES_MAX;
+    if (st < 2) return -1;
+    P.stages = st;
+    const size_t smem = (size_t)st * stage_b + fixed;
+
+    const long n_chunks = (rows + KC - 1) / KC;
+    const int tiles = P.m_tiles * P.n_tiles;
+    long splits = rsb_sm_count() / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > (n_chunks + 3) / 4) splits = (n_chunks + 3) / 4;      // at least ~4 chunks of reduction per flush
+    if (splits < 1) splits = 1;
+    P.splits = (int)splits;
+
+    // piece maps: the column coordinate is the stored tensor's own column index (see piece0_col)
+    auto maps = [&](const Opnd &O, CUtensorMap *m0, CUtensorMap *m1) {
+        const long ext0 = O.kind == RSB_OPND_AFFINE2 ? O.ku : (long)O.k0 + O.K;
+        if (make_map(m0, O.U, ext0, rows, O.ldu, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+        if (O.kind == RSB_OPND_DUAL_BN_RELU)
+            return make_map(m1, O.U + O.ku, (long)O.k0 + O.K, rows, O.ldu, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (O.kind == RSB_OPND_AFFINE2)
+            return make_map(m1, O.V, (long)O.k0 + O.K, rows, O.ldv, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        return 0;
+    };
+    if (maps(*G, &P.mapG0, &P.mapG1) || maps(*X, &P.mapX0, &P.mapX1)) return (int)cudaErrorInvalidValue;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        RSB_CUDA(cudaFuncSetAttribute(gemm_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        attr_set = true;
+    }
+    gemm_wgrad2_kernel<<<tiles * P.splits, THREADS2, smem, stream>>>(P);
+    RSB_CHECK_LAUNCH("gemm_wgrad2_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}

@@ -209,13 +209,8 @@ class _FusedSAMLP(Function):
             dZ = torch.empty(R, Cp, device=dev)
             stp = st_parts.pop(0)
             scp, shp, mup, invp = coefs[l - 1]
-            if Cp % 4 == 0:
-                # plain tensor-core dgrad, then one bandwidth-bound pass: ReLU mask + BatchNorm-backward statistics
-                gemm_rows(R, Cp, Gop, WpT, Y=dZ)
-                N.call("rsb_bn_relu_backward", R, Cp, dZ, dZ.stride(0), Ys[l - 1], Ys[l - 1].stride(0), scp, shp, mup, invp,
-                       1 if dual else 0, stp)
-            else:
-                gemm_rows(R, Cp, Gop, WpT, Y=dZ, stats=stp, mask=(Ys[l - 1], scp, shp, mup, invp, dual))
+            # dgrad with the ReLU mask of layer l-1 and its BatchNorm-backward statistics fused into the epilogue
+            gemm_rows(R, Cp, Gop, WpT, Y=dZ, stats=stp, mask=(Ys[l - 1], scp, shp, mup, invp, dual))
             width = 2 * Cp if dual else Cp
             cop = torch.empty(5, width, device=dev)
             N.call("rsb_bn_backward_coef", Cp, R, stp, 1 if dual else 0, scp, mup, invp, cop[0], cop[1], cop[2], cop[3], cop[4])

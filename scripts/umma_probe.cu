@@ -183,6 +183,22 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     }
 }
 
+__global__ void dump_kernel(const __grid_constant__ CUtensorMap map, float *out)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect(&bar, 4096);
+        tma_load_2d(smem, &map, 0, 0, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = ((float *)smem)[i];
+}
+
 static float tfx(int i) { return (float)((i * 37 + 11) % 17 - 8) * 0.25f; }   // tf32-exact values
 
 int main()
@@ -195,6 +211,32 @@ int main()
     CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
 
     int fails = 0;
+    {   // physical placement of a 32-channel x 32-row box under the 32-byte-atom swizzle: element (r, c) = 100 r + c
+        std::vector<float> h(32 * 32), o(1024);
+        for (int r = 0; r < 32; r++) for (int c = 0; c < 32; c++) h[r * 32 + c] = 100.f * r + c;
+        float *d, *dout;
+        CK(cudaMalloc(&d, 4096)); CK(cudaMalloc(&dout, 4096));
+        CK(cudaMemcpy(d, h.data(), 4096, cudaMemcpyHostToDevice));
+        CUtensorMap m = make_map(d, 32, 32, 32, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        CK(cudaFuncSetAttribute(dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192));
+        dump_kernel<<<1, 128, 8192>>>(m, dout);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(o.data(), dout, 4096, cudaMemcpyDeviceToHost));
+        printf("ATOM_32B placement: smem row r, 16-byte chunk p holds channels starting at:\n");
+        int bad = 0;
+        for (int r = 0; r < 32; r++) {
+            if (r < 9) printf("  row %2d:", r);
+            for (int p = 0; p < 8; p++) {
+                const float v = o[r * 32 + p * 4];
+                const int rr = (int)(v / 100.f), c = (int)(v - 100.f * rr);
+                if (r < 9) printf(" %2d%s", c, rr == r ? "" : "!");
+                if (rr != r || c != ((p ^ ((r & 3) << 1)) * 4)) bad++;
+            }
+            if (r < 9) printf("\n");
+        }
+        printf("%s placement == chunk ^ ((row & 3) << 1) : %d mismatches\n", bad ? "FAIL" : "PASS", bad);
+        cudaFree(d); cudaFree(dout);
+    }
     // ---------------- K-major cases: A [rowsA, ldA] logical K = Kv columns, B [64, 32]
     struct KCase { const char *name; int lbo, sbo, rewrite, store, Kv, rowsA, a_c1, rowsD, colsD; };
     KCase kc[] = {
