@@ -33,6 +33,10 @@ void rsb_reset_launch_count(void);
 
 /* ------------------------------------------------------------------ dense layout (classification) */
 
+/* FPS kernel generation for multi-CTA (cluster) plans: 0 (default) = per-sample exchange by st.async messages completing
+ * on the destination's mbarrier; 1 = one barrier.cluster per sample (round-1 kernel).  Results are identical. */
+void rsb_fps_set_generation(int gen);
+
 /* replaces furthestsampling_cuda_launcher(b,n,m,dataset,temp,idxs)      cls/po/src/sampling/sampling_cuda_kernel.h:19
  * xyz [b,n,3]; temp [b,n] scratch or NULL (no need to pre-fill; final running minima are written back
  * when given); idx [b,m] int32, idx[:,0] = 0.  new_xyz: optional [b,m,3] fused gather of the sampled
@@ -97,6 +101,13 @@ int rsb_interpolation_backward(int b, int c, int n, int m, const float *grad_out
  * callers whose segment sizes are produced on the GPU (sectorized FPS) need no host synchronisation. */
 int rsb_furthestsampling_packed(int b, int n_max, const int *n_max_dev, const float *xyz, const int *offset,
                                 const int *new_offset, float *tmp, int *idx, float *new_xyz, cudaStream_t stream);
+/* Same, when the host knows only bounds on the segment sizes (the sectorized FPS of seg/po/functions/pointops.py:52-111
+ * computes its sector sizes on the device): segments of up to ~n_expect points take a launch planned for n_expect, the
+ * rest a second launch planned for n_limit (>= every segment).  No host synchronisation; results identical to
+ * rsb_furthestsampling_packed.  n_max_dev as above (may be NULL when every launch has a segment of >= 1024 points). */
+int rsb_furthestsampling_packed_bounded(int b, int n_expect, int n_limit, const int *n_max_dev, const float *xyz,
+                                        const int *offset, const int *new_offset, float *tmp, int *idx, float *new_xyz,
+                                        cudaStream_t stream);
 
 /* replaces knnquery_cuda_launcher(m,nsample,xyz,new_xyz,offset,new_offset,idx,dist2)   seg/po/src/knnquery/knnquery_cuda_kernel.h:11
  * adds b (= number of clouds).  dist [m,nsample]: squared distances, or their square roots when sqrt_out != 0

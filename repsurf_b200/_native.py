@@ -33,6 +33,7 @@ _SIGS = {
     "rsb_interpolation_forward": [_i, _i, _i, _i, _p, _p, _p, _p],
     "rsb_interpolation_backward": [_i, _i, _i, _i, _p, _p, _p, _p],
     "rsb_furthestsampling_packed": [_i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "rsb_furthestsampling_packed_bounded": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],
     "rsb_knnquery_grid": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _l],
     "rsb_umbrella_features": [_l, _i, _i, _i, _i, _p, _p, _p, _p],
@@ -60,7 +61,7 @@ _SIGS = {
     "rsb_pool_bn_backward_dense": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
-                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation"])
+                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation", "rsb_fps_set_generation"])
 
 
 def build(force=False):
@@ -91,6 +92,8 @@ def lib():
         L.rsb_linear_tc_weight_floats.argtypes = [_i, _i]
         L.rsb_knn_grid_workspace_bytes.restype = _l
         L.rsb_knn_grid_workspace_bytes.argtypes = [_i, _i]
+        L.rsb_fps_set_generation.restype = None
+        L.rsb_fps_set_generation.argtypes = [_i]
         L.rsb_tc_set_generation.restype = None
         L.rsb_tc_set_generation.argtypes = [_i]
         _lib = L

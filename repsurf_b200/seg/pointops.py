@@ -19,8 +19,9 @@ from .. import _native as N
 # kNN: clouds with at least this many points (on average) go through the grid search; None = always all-pairs
 KNN_GRID_MIN_POINTS = 2048
 
-# sectorized FPS: keep the sector sizes on the device (no host sync, larger launch) or read back their maximum
-SECTOR_SIZES_ON_DEVICE = False
+# largest segment (in priority positions) the FPS kernel keeps in registers: 16 CTAs x 512 threads x 16 points; beyond
+# it the kernel streams the running minima through a scratch buffer the caller provides
+_FPS_REGISTER_CAPACITY = 16 * 512 * 16
 
 # ---------------------------------------------------------------------------------------------
 # host copies of offset tensors
@@ -81,7 +82,9 @@ class FurthestSampling(Function):
         off, noff = host_offsets(offset), host_offsets(new_offset)
         b = len(off)
         idx = torch.empty(noff[-1], dtype=torch.int32, device=xyz.device)
-        N.call("rsb_furthestsampling_packed", b, max(_sizes(off)), None, xyz, offset, new_offset, None, idx, None)
+        n_max = max(_sizes(off))
+        tmp = torch.empty(xyz.shape[0], device=xyz.device) if n_max + 1024 > _FPS_REGISTER_CAPACITY else None
+        N.call("rsb_furthestsampling_packed", b, n_max, None, xyz, offset, new_offset, tmp, idx, None)
         ctx.mark_non_differentiable(idx)
         return idx
 
@@ -151,15 +154,17 @@ class SectorizedFurthestSampling(Function):
         sector_offset = counts.cumsum(0).to(torch.int32)
         sector_xyz = xyz[order].contiguous()
         idx = torch.empty(noff[-1], dtype=torch.int32, device=dev)
-        if SECTOR_SIZES_ON_DEVICE:
-            # fully asynchronous: the launch is sized for the whole cloud, the tie rule comes from the device scalar
-            n_max_dev = counts.max().to(torch.int32).reshape(1)
-            N.call("rsb_furthestsampling_packed", nseg, max(sizes), n_max_dev, sector_xyz, sector_offset,
-                   new_sector_offset, None, idx, None)
-        else:
-            # one scalar read-back buys a launch sized for the largest SECTOR (4x fewer register slots per thread)
-            N.call("rsb_furthestsampling_packed", nseg, int(counts.max()), None, sector_xyz, sector_offset,
-                   new_sector_offset, None, idx, None)
+        # The sector sizes exist on the device only.  No read-back: sectors of up to 1.1x the mean size take a launch
+        # planned for that size, anything larger a second launch planned for the whole cloud (it exits at once when the
+        # sectors are balanced) - rsb_furthestsampling_packed_bounded.  The reference's tie rule depends on the largest
+        # sector only through min(2^floor(log2 n_max), 1024): known on the host whenever some sector must hold >= 1024
+        # points (pigeonhole), else taken from the device-side maximum.
+        mean_sector = max(-(-sz // k) for sz, k in zip(sizes, nsec))
+        n_expect = min(max(sizes), mean_sector + mean_sector // 10 + 1)
+        n_max_dev = None if mean_sector >= 1024 else counts.max().to(torch.int32).reshape(1)
+        tmp = torch.empty(n, device=dev) if max(sizes) + 1024 > _FPS_REGISTER_CAPACITY else None
+        N.call("rsb_furthestsampling_packed_bounded", nseg, n_expect, max(sizes), n_max_dev, sector_xyz, sector_offset,
+               new_sector_offset, tmp, idx, None)
         out = order[idx.long()]
         ctx.mark_non_differentiable(out)
         return out

@@ -337,7 +337,14 @@ class _LinearBN(Function):
         return dX, dW.reshape(ctx.w_shape), db, co[3], co[4], None, None
 
 
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
 class _Linear(Function):
+    """Y = X W^T + b.  Output and incoming gradient live in row-padded buffers (pitch a multiple of 4 floats) so that
+    the narrow classifier head (13 classes) stays on the TMA-fed kernels; the caller sees a [R, N] view."""
+
     @staticmethod
     def forward(ctx, X, W, bias):
         X = X.contiguous()
@@ -345,18 +352,21 @@ class _Linear(Function):
         Nn = W.shape[0]
         W2 = W.detach().contiguous()
         Wp, _, _ = prep_weight(W2)
-        Y = torch.empty(R, Nn, device=X.device)
-        gemm_rows(R, Nn, opnd(OPND_RAW, X, K), Wp, Y=Y, bias=None if bias is None else bias.detach())
+        Ybuf = torch.empty(R, _pad4(Nn), device=X.device)
+        gemm_rows(R, Nn, opnd(OPND_RAW, X, K), Wp, Y=Ybuf, bias=None if bias is None else bias.detach())
         ctx.saved = (X, W2)
         ctx.has_bias = bias is not None
-        return Y
+        return Ybuf[:, :Nn]
 
     @staticmethod
     def backward(ctx, dY):
         X, W2 = ctx.saved
         R, K = X.shape
         Nn = W2.shape[0]
-        dY = dY.contiguous()
+        if dY.stride(1) != 1 or dY.stride(0) % 4 or dY.data_ptr() % 16:
+            buf = torch.empty(R, _pad4(Nn), device=X.device)
+            buf[:, :Nn].copy_(dY)
+            dY = buf[:, :Nn]
         dW = torch.zeros(Nn, K, device=X.device)
         gemm_wgrad(R, opnd(OPND_RAW, dY, Nn), opnd(OPND_RAW, X, K), dW)
         dX = None

@@ -1,6 +1,7 @@
 """GPU parity suite (-m gpu): every CUDA operator, called through the C-ABI, against the CPU oracle on the same
 seeded inputs (bit-exact for indices), against the reference's own CUDA kernels (oracle/_ref) when present,
 and size-independent properties at the full BASELINE sizes."""
+import math
 import os
 
 import numpy as np
@@ -88,31 +89,59 @@ def test_fps_packed_matches_oracle(sizes, stride):
     assert torch.equal(got, want)
 
 
-def test_sectorized_fps_device_side_sizes(monkeypatch):
-    P = _seg()
-    xyz, off = _packed((12000, 3000, 10500), 8)
-    xyz = (xyz - xyz.mean(0)).to(cuda)
-    noff = torch.tensor(np.cumsum([3000, 750, 2625]), dtype=torch.int32)
-    a = P.sectorized_fps(xyz, off.to(cuda), noff.to(cuda), 4)
-    monkeypatch.setattr(P, "SECTOR_SIZES_ON_DEVICE", True)
-    b = P.sectorized_fps(xyz, off.to(cuda), noff.to(cuda), 4)
-    assert torch.equal(a, b)
+def _edge_safe(xyz, off, num_sectors, min_points=10000, margin=1e-4):
+    """Nudge (rotate about z) every point whose azimuth lies within `margin` of an inner sector edge, so that the
+    sector membership cannot depend on a last-ulp difference between the CPU and CUDA atan2 / linspace."""
+    xyz = xyz.clone()
+    for _ in range(8):
+        bad_total, start = 0, 0
+        for end in off.tolist():
+            pts = xyz[start:end]
+            if end - start >= min_points:
+                ang = torch.atan2(pts[:, 0], pts[:, 1])
+                edges = torch.linspace(float(ang.min()), float(ang.max()) + 1e-4, num_sectors + 1)[1:-1]
+                bad = ((ang[:, None] - edges[None, :]).abs() < margin).any(1)
+                # never move the two extreme points (they define the edges)
+                bad[ang.argmin()] = False
+                bad[ang.argmax()] = False
+                if bad.any():
+                    c, s_ = math.cos(3e-4), math.sin(3e-4)
+                    x, y = pts[bad, 0].clone(), pts[bad, 1].clone()
+                    pts[bad, 0], pts[bad, 1] = c * x - s_ * y, s_ * x + c * y
+                    bad_total += int(bad.sum())
+            start = end
+        if bad_total == 0:
+            return xyz
+    raise AssertionError("could not move the points off the sector edges")
 
 
-def test_sectorized_fps_matches_oracle():
+@pytest.mark.parametrize("skew", [False, True])
+def test_sectorized_fps_matches_oracle(skew):
+    """skew: 70 % of the first cloud sits in one sector, so its largest sector exceeds the 1.1x-mean capacity of the
+    first launch and goes through the follow-up launch of rsb_furthestsampling_packed_bounded."""
     xyz, off = _packed((12000, 3000, 10500), 8)
     xyz = xyz - xyz.mean(0)
+    if skew:
+        g = torch.Generator().manual_seed(11)
+        phi = torch.rand(8400, generator=g) * 1.2 + 0.1             # azimuth atan2(x, y) in a 1.2 rad wedge
+        r = torch.rand(8400, generator=g) * 4 + 0.5
+        xyz[:8400, 0], xyz[:8400, 1] = r * torch.sin(phi), r * torch.cos(phi)
+    xyz = _edge_safe(xyz, off, 4)
     noff = torch.tensor(np.cumsum([3000, 750, 2625]), dtype=torch.int32)
     want = O.sectorized_fps(xyz, off, noff, 4)
     got = _seg().sectorized_fps(xyz.to(cuda), off.to(cuda), noff.to(cuda), 4).cpu()
     assert got.dtype == torch.int64
-    if not torch.equal(got, want):
-        # CPU vs CUDA atan2 may differ in the last ulp for a point sitting on a sector edge; then the two
-        # sector memberships differ by that point and the picks inside two sectors may legitimately change.
-        ang = torch.atan2(xyz[:, 0], xyz[:, 1])
-        ang_gpu = torch.atan2(xyz[:, 0].to(cuda), xyz[:, 1].to(cuda)).cpu()
-        assert not torch.equal(ang, ang_gpu), "indices differ although the azimuths are bit-identical"
-        pytest.skip("CPU/CUDA atan2 differ by an ulp on this input; exact comparison impossible")
+    assert torch.equal(got, want)
+
+
+def test_sectorized_fps_small_clouds_use_device_maximum():
+    """clouds below min_points are single sectors; with every cloud under 1024 points the reference's block size
+    (tie rule) follows the largest one, which only the device knows when sizes come from the sector split."""
+    xyz, off = _packed((700, 300, 900), 5)
+    noff = torch.tensor(np.cumsum([175, 75, 225]), dtype=torch.int32)
+    want = O.sectorized_fps(xyz, off, noff, 4)
+    got = _seg().sectorized_fps(xyz.to(cuda), off.to(cuda), noff.to(cuda), 4).cpu()
+    assert torch.equal(got, want)
 
 
 # ------------------------------------------------------------------------------------------- ball query
