@@ -179,105 +179,133 @@ def peaks():
 
 
 # -------------------------------------------------------------------------------------------- CPU arm
-def cpu_port_run(workload, steps, warmup, sample_clouds, sample_n):
-    """fwd+bwd of the oracle port on the host cores over a bounded sample; returns (clouds/s, seconds/step, cores)."""
+CPU_SAMPLE = {"seg": (2, 40960), "cls": (32, 1024)}
+
+
+def cpu_port_inner(workload, steps, warmup, threads):
+    """Runs INSIDE the child process started by cpu_arm (one thread pool of `threads`, passive OpenMP waiting): fwd+bwd of
+    the oracle port (oracle/model_ref.py over the OpenMP C oracle) on the bounded sample; prints seconds per step."""
     from oracle import model_ref as MR
-    from oracle import oracle as O
-    torch.set_num_threads(os.cpu_count())
-    cores = max(torch.get_num_threads(), O.num_threads())
+    torch.set_num_threads(threads)
     torch.manual_seed(0)
     np.random.seed(0)
+    clouds, n = CPU_SAMPLE[workload]
     if workload == "seg":
         model = MR.SegNet().train()
-        coord, feat, offset, target = make_inputs("seg", sample_clouds, sample_n, 0, False)
+        coord, feat, offset, target = make_inputs("seg", clouds, n, 0, False)
         crit = nn.CrossEntropyLoss()
+
         def step():
             model.zero_grad(set_to_none=True)
             crit(model([coord, feat, offset]), target).backward()
     else:
         from repsurf_b200.models import SmoothClsLoss
         model = MR.ClsNet().train()
-        pts, target = make_inputs("cls", sample_clouds, sample_n, 0, False)
+        pts, target = make_inputs("cls", clouds, n, 0, False)
         crit = SmoothClsLoss()
+
         def step():
             model.zero_grad(set_to_none=True)
             crit(model(pts), target).backward()
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
+    ts = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return sample_clouds / dt, dt, cores
+        ts.append(time.perf_counter() - t0)
+    print("CPU_PORT_RESULT " + json.dumps({"threads": threads, "sec": ts}), flush=True)
 
 
-# -------------------------------------------------------------------------------------------- main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("RSB_WORKLOAD", "seg"), choices=list(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+def cpu_arm(workload, steps):
+    """The reference's CPU path for this workload = the oracle port, timed on the host cores.
+    Each candidate thread count runs in its OWN process with ONE pool of that size (OMP_NUM_THREADS = torch threads,
+    OMP_WAIT_POLICY=passive): round 1 ran torch's 128 intra-op threads and 128 spinning OpenMP threads in one process and
+    was 37x slower than the same code with one thread.  Result: best step over all candidates (best-of-k), with the
+    thread count that achieved it."""
+    cores = os.cpu_count() or 1
+    cands = sorted({min(cores, 8), min(cores, 32), cores})
+    clouds, n = CPU_SAMPLE[workload]
+    tried, best = {}, None
+    for t in cands:
+        env = dict(os.environ)
+        env.update({"OMP_NUM_THREADS": str(t), "MKL_NUM_THREADS": str(t), "OMP_WAIT_POLICY": "passive", "GOMP_SPINCOUNT": "0",
+                    "OMP_PROC_BIND": "false", "CUDA_VISIBLE_DEVICES": ""})
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-inner", "--workload", workload,
+               "--steps", str(steps), "--warmup", "1", "--threads", str(t)]
+        try:
+            out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600).stdout
+            line = [l for l in out.splitlines() if l.startswith("CPU_PORT_RESULT ")][-1]
+            sec = json.loads(line[len("CPU_PORT_RESULT "):])["sec"]
+        except Exception:
+            continue
+        tried[str(t)] = round(clouds / min(sec), 4)
+        if best is None or min(sec) < best[0]:
+            best = (min(sec), t)
+    if best is None:
+        raise RuntimeError("the CPU port did not run")
+    dt, threads = best
+    desc = (f"{clouds} cloud(s) x N={n} of the same workload, fwd+bwd, best of {steps} step(s) after 1 warm-up, "
+            f"one pool of {threads} threads (of {cores} cores; clouds/s by thread count: {tried})")
+    return {"value": clouds / dt, "unit": "clouds/s", "cores": threads, "kind": "port", "sample": desc,
+            "sec_per_step": dt, "host_cores": cores, "tried": tried}
 
-    rank = int(os.environ.get("RANK", 0))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    wl = WORKLOADS[args.workload]
-    metric = "clouds/sec fwd+bwd RepSurf-U"
-    sample = dict(seg=(1, 40960), cls=(8, 1024))[args.workload]
 
-    # ---------------- reference arm: the CPU port on the host cores (rank 0 only) ----------------
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        steps = max(1, min(args.steps, 3))
-        warm = 1 if args.warmup > 0 else 0
-        v, dt, cores = cpu_port_run(args.workload, steps, warm, *sample)
-        desc = f"{sample[0]} cloud(s) x N={sample[1]} of the same workload, fwd+bwd, {steps} step(s)"
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": v, "unit": "clouds/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"], "sample": desc},
-            "cpu_baseline": {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port", "sample": desc},
-            "e2e": {"value": v, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
+# -------------------------------------------------------------------------------------------- our arm
+TIMED_ENTRIES = {"rsb_furthestsampling_packed", "rsb_furthestsampling_packed_bounded", "rsb_furthestsampling_dense",
+                 "rsb_knnquery_packed", "rsb_knnquery_dense", "rsb_knnquery_grid", "rsb_gemm_wgrad", "rsb_gemm_rows",
+                 "rsb_ballquery"}
 
-    # ---------------- our arm ---------------------------------------------------------------------
+
+def opnd_bytes(o, rows):
+    per_row = {0: o.K, 1: o.K, 2: 2 * o.K, 3: o.K + min(o.K, o.ku), 4: o.K}[o.kind]
+    return rows * per_row * 4
+
+
+def gemm_alg_bytes(name, a):
+    """algorithmic HBM bytes of one GEMM launch: every operand tensor read once, the result written once"""
+    if name == "rsb_gemm_wgrad":
+        return opnd_bytes(a[1], a[0]) + opnd_bytes(a[2], a[0]) + a[1].K * a[2].K * 4
+    return opnd_bytes(a[2], a[0]) + a[0] * a[1] * 4
+
+
+def gemm_desc(name, a):
+    if name == "rsb_gemm_wgrad":
+        return f"wgrad rows={a[0]} dW[{a[1].K}x{a[2].K}], operand kinds {a[1].kind}/{a[2].kind}"
+    return f"rows={a[0]} K={a[2].K} N={a[1]}, operand kind {a[2].kind}"
+
+
+def run_ours(workload, args, rank, local_rank, world, dev, full):
+    """Times `workload` (value: inputs resident; e2e: pinned host inputs + loss read-back).  full: also the per-entry
+    rooflines, launch count and clocks (primary workload only)."""
     import torch.distributed as dist
     from repsurf_b200 import _native
     from repsurf_b200.models import RepSurfCls, RepSurfSeg, SmoothClsLoss
     from repsurf_b200.seg import pointops as PS
+    from repsurf_b200.dist import FlatGrads, broadcast_module
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.allow_tf32 = False          # fp32-faithful MLP (north star: 1e-5 rel)
-    torch.backends.cuda.matmul.allow_tf32 = False
+    wl = WORKLOADS[workload]
     torch.manual_seed(rank)
     np.random.seed(rank)
-
-    model = (RepSurfSeg() if args.workload == "seg" else RepSurfCls()).to(dev).train()
-    crit = nn.CrossEntropyLoss() if args.workload == "seg" else SmoothClsLoss()
-    from repsurf_b200.dist import FlatGrads, broadcast_module
+    model = (RepSurfSeg() if workload == "seg" else RepSurfCls()).to(dev).train()
+    crit = nn.CrossEntropyLoss() if workload == "seg" else SmoothClsLoss()
     params = [p for p in model.parameters()]
     broadcast_module(model)
     # gradients are packed into one flat buffer after backward: ONE all-reduce per step (3.9 MB seg / 5.9 MB cls)
     fg = FlatGrads(params)
     opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4)
 
-    host = make_inputs(args.workload, wl["clouds"], wl["n"], 100 + rank, pin=True)
+    host = make_inputs(workload, wl["clouds"], wl["n"], 100 + rank, pin=True)
     devin = [t.to(dev) for t in host]
-    if args.workload == "seg":
+    if workload == "seg":
         PS.register_offsets(devin[2], host[2].tolist())
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
     def fwd_bwd(inp):
         fg.zero()
-        if args.workload == "seg":
+        if workload == "seg":
             loss = crit(model([inp[0], inp[1], inp[2]]), inp[3])
         else:
             loss = crit(model(inp[0]), inp[1])
@@ -291,7 +319,7 @@ def main():
 
     def step_e2e():
         inp = [t.to(dev, non_blocking=True) for t in host]
-        if args.workload == "seg":
+        if workload == "seg":
             PS.register_offsets(inp[2], host[2].tolist())   # the host already holds the offsets it uploads
         loss = fwd_bwd(inp)
         return float(loss)                                   # D2H read of the step's result
@@ -317,132 +345,220 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
     clocks = ClockSampler(local_rank)
-    if rank == 0 and not os.environ.get("RSB_NO_CLOCKS"):
+    if full and rank == 0 and not os.environ.get("RSB_NO_CLOCKS"):
         clocks.start()
     _native.reset_launch_count()
-    timed_entries = None if os.environ.get("RSB_TIME_ALL_ENTRIES") else {
-        "rsb_furthestsampling_packed", "rsb_furthestsampling_dense", "rsb_knnquery_packed", "rsb_knnquery_dense",
-        "rsb_knnquery_grid", "rsb_gemm_wgrad", "rsb_gemm_rows", "rsb_ballquery"}
-    with EntryTimer(_native, timed_entries) as et:
+    timed_entries = None if os.environ.get("RSB_TIME_ALL_ENTRIES") else TIMED_ENTRIES
+    if full:
+        with EntryTimer(_native, timed_entries) as et:
+            ms_step = timed(step_resident, args.steps)
+        per_entry = et.summary()
+    else:
         ms_step = timed(step_resident, args.steps)
+        per_entry = {}
     launches = _native.launch_count()
-    per_entry = et.summary()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if (full and rank == 0) else None
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    # work counters of the grid kNN: ONE extra untimed step (the counting adds an atomic per query)
+    knn_work = None
+    if full and workload == "seg":
+        ctr = torch.zeros(3, dtype=torch.int64, device=dev)
+        _native.lib().rsb_knn_grid_set_counters(ctr.data_ptr())
+        step_resident()
+        torch.cuda.synchronize()
+        _native.lib().rsb_knn_grid_set_counters(None)
+        knn_work = [int(v) for v in ctr.tolist()]
 
     clouds_total = wl["clouds"] * world
-    value = clouds_total / (ms_step * 1e-3)
-    e2e_value = clouds_total / (ms_e2e * 1e-3)
+    res = {"workload": wl["name"], "value": clouds_total / (ms_step * 1e-3), "ms_per_step": ms_step,
+           "e2e": {"value": clouds_total / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+           "gpu_launches": int(launches), "clocks": clk, "per_entry": per_entry, "knn_work": knn_work}
+    del model, opt, fg, devin
+    torch.cuda.empty_cache()
+    return res
 
-    # ---- rooflines: every timed C-ABI entry against its own bound; "roofline" = the entry with the most time ----
+
+def build_rooflines(per_entry, knn_work, ms_step, steps, workload):
+    wl = WORKLOADS[workload]
     hbm_peak, tf_peak, peak_src = peaks()
-    entry_share = {k: round(v["ms"] / (ms_step * args.steps), 4) for k, v in per_entry.items()}
-    dom = max(per_entry.items(), key=lambda kv: kv[1]["ms"]) if per_entry else None
+    entry_share = {k: round(v["ms"] / (ms_step * steps), 4) for k, v in per_entry.items()}
+    rooflines = {}
 
     def biggest(v):
         big = max(t for _a, t in v["each"])
         sel = [(a, t) for a, t in v["each"] if t > 0.6 * big]
         return sel[0][0], float(np.mean([t for _a, t in sel]))
 
-    def opnd_bytes(o, rows):
-        per_row = {0: o.K, 1: o.K, 2: 2 * o.K, 3: o.K + min(o.K, o.ku), 4: o.K}[o.kind]
-        return rows * per_row * 4
+    # ---- GEMMs: per shape (launches of one shape averaged), then the heaviest shape per entry, the time-weighted total of
+    # ALL launches of both entries, and the worst shape among those that matter (>= 2 % of the GEMM time)
+    shapes = {}
+    for name in ("rsb_gemm_rows", "rsb_gemm_wgrad"):
+        for a, t in per_entry.get(name, {"each": []})["each"]:
+            key = (name, gemm_desc(name, a))
+            d = shapes.setdefault(key, {"bytes": gemm_alg_bytes(name, a), "ms": 0.0, "n": 0,
+                                        "flops": 2.0 * a[0] * (a[1].K * a[2].K if name == "rsb_gemm_wgrad" else a[1] * a[2].K)})
+            d["ms"] += t
+            d["n"] += 1
+    gemm_ms = sum(d["ms"] for d in shapes.values())
+    for name, kern in (("rsb_gemm_rows", "gemm_rows2_kernel (TMA-fed tcgen05 3xTF32)"), ("rsb_gemm_wgrad", "gemm_wgrad2_kernel (TMA-fed tcgen05 3xTF32)")):
+        mine = {k: d for k, d in shapes.items() if k[0] == name}
+        if not mine:
+            continue
+        k, d = max(mine.items(), key=lambda kd: kd[1]["bytes"])
+        t_ms = d["ms"] / d["n"]
+        ach = d["bytes"] / (t_ms * 1e-3) / 1e9
+        rooflines[name] = {"kernel": kern, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                           "launch_ms": t_ms, "launch": k[1] + " (the shape that moves the most bytes)",
+                           "algorithmic_bytes_per_launch": d["bytes"], "algorithmic_tflops": d["flops"] / (t_ms * 1e-3) / 1e12}
+    if shapes:
+        tot_b = sum(d["bytes"] * d["n"] for d in shapes.values())
+        ach = tot_b / (gemm_ms * 1e-3) / 1e9
+        rooflines["gemm_total"] = {"kernel": "all gemm_rows + gemm_wgrad launches of the timed steps", "bound": "hbm", "achieved": ach,
+                                   "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "launch_ms": gemm_ms / steps,
+                                   "launch": f"{sum(d['n'] for d in shapes.values()) // steps} launches per step, time-weighted",
+                                   "algorithmic_bytes_per_launch": tot_b / steps,
+                                   "algorithmic_tflops": sum(d["flops"] * d["n"] for d in shapes.values()) / (gemm_ms * 1e-3) / 1e12}
+        heavy = {k: d for k, d in shapes.items() if d["ms"] >= 0.02 * gemm_ms}
+        k, d = min(heavy.items(), key=lambda kd: kd[1]["bytes"] * kd[1]["n"] / kd[1]["ms"])
+        t_ms = d["ms"] / d["n"]
+        ach = d["bytes"] / (t_ms * 1e-3) / 1e9
+        rooflines["gemm_worst"] = {"kernel": k[0], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                   "launch_ms": t_ms, "launch": k[1] + f" (lowest fraction among shapes with >= 2 % of the GEMM time; "
+                                   f"{round(100 * d['ms'] / gemm_ms, 1)} % of it)", "algorithmic_bytes_per_launch": d["bytes"]}
 
-    def most_bytes(v, alg_of):
-        """GEMM entries run at many shapes per step: report the launch shape that moves the most algorithmic bytes
-        (the one the ncu traffic capture in profiles/ holds), averaged over its launches."""
-        best = max(v["each"], key=lambda at: alg_of(at[0]))[0]
-        key = alg_of(best)
-        ts = [t for a_, t in v["each"] if alg_of(a_) == key and a_[0] == best[0]]
-        return best, float(np.mean(ts))
-
-    rooflines = {}
     for name, v in per_entry.items():
-        a, t_ms = biggest(v)
-        if name == "rsb_gemm_wgrad":
-            a, t_ms = most_bytes(v, lambda x: opnd_bytes(x[1], x[0]) + opnd_bytes(x[2], x[0]))
-        elif name == "rsb_gemm_rows":
-            a, t_ms = most_bytes(v, lambda x: opnd_bytes(x[2], x[0]) + x[0] * x[1] * 4)
         if name.startswith("rsb_furthestsampling"):
-            if name.endswith("packed"):
-                nseg, n_max = a[0], a[1]
-                m_seg = (wl["n"] // 4 // 4) if (args.workload == "seg" and nseg == wl["clouds"] * 4) else n_max // 4
-                alg = nseg * fps_algorithmic_bytes(n_max if nseg != wl["clouds"] * 4 else wl["n"] / 4, m_seg)
-                note = f"{nseg} segments, largest {n_max} points, ~{m_seg} samples each (streaming model, SURVEY 8d)"
+            a, t_ms = biggest(v)
+            if name.endswith("dense"):
+                nseg, n_seg, m_seg = a[0], a[1], a[2]
+            elif name.endswith("bounded"):          # sectorized FPS: nseg sectors of ~n/4 points
+                nseg = a[0]
+                n_seg, m_seg = wl["n"] * wl["clouds"] // nseg, wl["n"] // 4 * wl["clouds"] // nseg
             else:
-                alg = a[0] * fps_algorithmic_bytes(a[1], a[2])
-                note = f"{a[0]} clouds {a[1]} -> {a[2]} (streaming model, SURVEY 8d)"
+                nseg, n_seg = a[0], a[1]
+                m_seg = n_seg // 4
+            alg = nseg * fps_algorithmic_bytes(n_seg, m_seg)
             ach = alg / (t_ms * 1e-3) / 1e9
-            rooflines[name] = {"kernel": "fps_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": ach / hbm_peak, "launch_ms": t_ms, "launch": note, "algorithmic_bytes_per_launch": alg}
-        elif name == "rsb_gemm_wgrad":
-            rows_, G_, X_ = a[0], a[1], a[2]
-            alg = opnd_bytes(G_, rows_) + opnd_bytes(X_, rows_) + G_.K * X_.K * 4
-            flops = 2.0 * rows_ * G_.K * X_.K
-            ach = alg / (t_ms * 1e-3) / 1e9
-            rooflines[name] = {"kernel": "gemm_wgrad_kernel (tcgen05 3xTF32)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                               "unit": "GB/s", "frac": ach / hbm_peak, "launch_ms": t_ms,
-                               "launch": f"rows={rows_} dW[{G_.K}x{X_.K}], operand kinds {G_.kind}/{X_.kind}",
-                               "algorithmic_bytes_per_launch": alg, "algorithmic_tflops": flops / (t_ms * 1e-3) / 1e12}
-        elif name == "rsb_gemm_rows":
-            rows_, N_, A_ = a[0], a[1], a[2]
-            alg = opnd_bytes(A_, rows_) + rows_ * N_ * 4
-            ach = alg / (t_ms * 1e-3) / 1e9
-            rooflines[name] = {"kernel": "gemm_rows_kernel (tcgen05 3xTF32)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                               "unit": "GB/s", "frac": ach / hbm_peak, "launch_ms": t_ms,
-                               "launch": f"rows={rows_} K={A_.K} N={N_}, operand kind {A_.kind}",
-                               "algorithmic_bytes_per_launch": alg,
-                               "algorithmic_tflops": 2.0 * rows_ * N_ * A_.K / (t_ms * 1e-3) / 1e12}
-        elif name.startswith("rsb_knnquery"):
-            pairs = None
-            if name == "rsb_knnquery_grid":
-                n_tot, m_tot, b_ = a[5], a[6], a[2]
-                pairs = m_tot * (n_tot / max(b_, 1))
-                note = f"m={m_tot} queries x n={n_tot // max(b_, 1)} candidates/cloud, k={v['each'][0][0][7] if len(v['each'][0][0]) > 7 else '?'} (uniform-grid search)"
-            elif name == "rsb_knnquery_packed":
-                note = "all-pairs kernel (small clouds)"
-            if pairs:
-                fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # B200: 148 SMs x 128 FFMA lanes x 2 x 1.965 GHz
-                ach = pairs * 9 / (t_ms * 1e-3) / 1e12
-                rooflines[name] = {"kernel": "knn_grid_kernel", "bound": "fp32 (all-pairs model: 9 flop/pair)", "achieved": ach,
-                                   "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "launch_ms": t_ms, "launch": note,
-                                   "algorithmic_pairs_per_launch": pairs}
+            rooflines[name] = {"kernel": "fps2_kernel (cluster, st.async exchange)" if nseg * 0 == 0 else "", "bound": "hbm",
+                               "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "launch_ms": t_ms,
+                               "launch": f"{nseg} segments of ~{n_seg} points -> {m_seg} samples (streaming model of SURVEY 8d; the "
+                                         "kernel is register-resident and latency-bound, see us_per_sample)",
+                               "algorithmic_bytes_per_launch": alg, "us_per_sample": 1e3 * t_ms / max(m_seg, 1),
+                               "busy_sms_note": "one cluster of CTAs per segment: nseg x cluster size of 148 SMs"}
+        elif name == "rsb_knnquery_grid" and knn_work:
+            # all grid launches of a step together: the counters are per step
+            t_ms = v["ms"] / steps
+            cand, ranges, replays = knn_work
+            queries = sum(a[6] for a, _t in v["each"]) / steps
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # B200: 148 SMs x 128 FFMA lanes x 2 x 1.965 GHz
+            ach = cand * 9 / (t_ms * 1e-3) / 1e12
+            rooflines[name] = {"kernel": "knn_grid_kernel (+ grid build)", "bound": "fp32 (candidates actually evaluated x 9 flop)",
+                               "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "launch_ms": t_ms,
+                               "launch": f"{v['calls'] // steps} searches per step, {int(queries)} queries",
+                               "candidates_per_step": cand, "candidates_per_query": cand / max(queries, 1),
+                               "cell_ranges_per_query": ranges / max(queries, 1), "tie_replays_per_step": replays,
+                               "candidate_gbs": cand * 16 / (t_ms * 1e-3) / 1e9,
+                               "all_pairs_equivalent_gpairs_per_s": sum(a[6] * (a[5] / max(a[2], 1)) for a, _t in v["each"]) / steps / (t_ms * 1e-3) / 1e9}
     # measured DRAM traffic per launch from the committed ncu --set full capture of the same kernels
-    # (profiles/r01_ncu_full_seg_v2_traffic.json, produced by scripts/ncu_summary.py; seg workload shapes)
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_seg_v2_traffic.json")
-    if os.path.exists(tpath) and args.workload == "seg":
-        traffic = json.load(open(tpath))
-    fam = {"rsb_gemm_wgrad": "gemm_wgrad_kernel", "rsb_gemm_rows": "gemm_rows_kernel", "rsb_knnquery_grid": "knn_grid_kernel",
-           "rsb_furthestsampling_packed": "fps_kernel", "rsb_furthestsampling_dense": "fps_kernel"}
+    for cand_path in ("r02_ncu_full_seg_traffic.json", "r01_ncu_full_seg_v2_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", cand_path)
+        if os.path.exists(tpath) and workload == "seg":
+            traffic = json.load(open(tpath))
+            break
+    fam = {"rsb_gemm_wgrad": ("gemm_wgrad2_kernel", "gemm_wgrad_kernel"), "rsb_gemm_rows": ("gemm_rows2_kernel", "gemm_rows_kernel"),
+           "rsb_knnquery_grid": ("knn_grid_kernel",), "rsb_furthestsampling_packed": ("fps2_kernel", "fps_kernel"),
+           "rsb_furthestsampling_packed_bounded": ("fps2_kernel", "fps_kernel"), "rsb_furthestsampling_dense": ("fps2_kernel", "fps_kernel")}
     for name, r in rooflines.items():
-        t = traffic.get(fam.get(name, ""))
+        t = next((traffic[f] for f in fam.get(name, ()) if f in traffic), None)
         r["traffic"] = t["dram_bytes"] if t else None
         r["peak_source"] = peak_src
-    roof = dict(rooflines[dom[0]]) if dom and dom[0] in rooflines else None
+    return rooflines, entry_share
 
+
+# -------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("RSB_WORKLOAD", "seg"), choices=list(WORKLOADS) + ["micro"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-inner"])
+    ap.add_argument("--threads", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    metric = "clouds/sec fwd+bwd RepSurf-U"
+
+    if args.impl == "reference-inner":
+        cpu_port_inner(args.workload, args.steps, args.warmup, args.threads)
+        return
+    if args.workload == "micro":
+        from scripts.microbench import main as micro_main
+        micro_main()
+        return
+    wl = WORKLOADS[args.workload]
+
+    # ---------------- reference arm: the CPU port on the host cores (rank 0 only) ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb = cpu_arm(args.workload, steps)
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": cb["value"], "unit": "clouds/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": cb["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"], "sample": cb["sample"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- our arm ---------------------------------------------------------------------
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False          # fp32-faithful MLP (north star: 1e-5 rel)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    r = run_ours(args.workload, args, rank, local_rank, world, dev, full=True)
+    second = None
+    if not args.no_secondary:
+        other = "cls" if args.workload == "seg" else "seg"
+        second = run_ours(other, args, rank, local_rank, world, dev, full=False)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    rooflines, entry_share = build_rooflines(r["per_entry"], r["knn_work"], r["ms_per_step"], args.steps, args.workload)
+    dom = max(r["per_entry"].items(), key=lambda kv: kv[1]["ms"]) if r["per_entry"] else None
+    roof = dict(rooflines[dom[0]]) if dom and dom[0] in rooflines else None
     out = {
-        "metric": metric, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "metric": metric, "value": r["value"], "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": wl["name"], "clouds_per_gpu": wl["clouds"], "points_per_cloud": wl["n"], "parallelism": f"dp{world}",
                    "optimizer_step": "SGD momentum inside the timed region", "tf32": False,
                    "l2": "per-step working set (activations > 126 MB) exceeds L2; no explicit flush"},
-        "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines, "entry_time_share": entry_share,
-        "dominant_entry": dom[0] if dom else None, "clocks": clk,
+        "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": roof, "rooflines": rooflines,
+        "entry_time_share": entry_share, "dominant_entry": dom[0] if dom else None, "clocks": r["clocks"],
     }
+    if second is not None:
+        # BASELINE.json's other single-GPU configuration, same run, same timing rules (no per-entry breakdown)
+        out["secondary"] = {"metric": metric, "config": {"workload": second["workload"]}, "value": second["value"], "unit": "clouds/s",
+                            "ms_per_step": second["ms_per_step"], "e2e": second["e2e"], "gpu_launches": second["gpu_launches"],
+                            "n_gpus": world, "steps": args.steps}
     if not args.no_cpu_baseline:
-        v, dt, cores = cpu_port_run(args.workload, 1, 0, *sample)
-        out["cpu_baseline"] = {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port",
-                               "sample": f"{sample[0]} cloud(s) x N={sample[1]}, fwd+bwd, 1 step ({dt:.1f} s)"}
+        out["cpu_baseline"] = cpu_arm(args.workload, 2)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

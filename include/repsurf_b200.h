@@ -124,6 +124,9 @@ long rsb_knn_grid_workspace_bytes(int n_total, int b);
 int rsb_knnquery_grid(int packed, int heap, int b, int n, int m, int n_total, int m_total, int nsample,
                       const float *xyz, const float *new_xyz, const int *offset, const int *new_offset, int *idx,
                       float *dist, int sqrt_out, void *workspace, long workspace_bytes, cudaStream_t stream);
+/* measurement hook: a device buffer of 3 x uint64 that every grid search adds to (candidates evaluated, cell ranges
+ * scanned, queries resolved by the exact tie replay); NULL disables (default). */
+void rsb_knn_grid_set_counters(unsigned long long *dev_counters);
 
 /* replaces grouping_forward/backward_cuda_launcher(m,nsample,c,...)                    seg/po/src/grouping/grouping_cuda_kernel.h:11-12
  * input [n,c], idx [m,nsample] -> output [m,nsample,c]. */
@@ -160,9 +163,10 @@ int rsb_segment_minmax(int b, long n_max, const float *values, const int *offset
  * GLOBAL row ids; flip [np] = +-1 per point (the per-cloud random inversion) or NULL; out [np, G, 10] with
  * G = k - (skip_first ? 1 : 0).  skip_first drops the query itself (classification); rotate_key sorts by the azimuth of
  * the rotated offsets (segmentation 'fix'); order_seg selects the channel order [polar,normal,pos,centroid] (else
- * [centroid,polar,normal,pos]). */
+ * [centroid,polar,normal,pos]).  out has row pitch ld >= 10 floats per triangle: the first `channels` (10, or 9 = the
+ * classification tree without return_dist, cls/modules/repsurface_utils.py:291-292) descriptor channels, zeros behind. */
 int rsb_umbrella_features(long np, int k, int skip_first, int rotate_key, int order_seg, const float *xyz, const int *idx,
-                          const float *flip, float *out, cudaStream_t stream);
+                          const float *flip, float *out, int channels, int ld, cudaStream_t stream);
 
 /* Umbrella MLP of the segmentation tree, Conv1d(10,10) + BatchNorm(train) + ReLU + Conv1d(10,10) + sum over the g
  * triangles of a point (segmentation/modules/repsurface_utils.py:297-302, :322-327), fused and recomputing: only the
@@ -246,7 +250,11 @@ int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, float *d
  * rsb_pool_forward: out[g,c] = max_s relu(sc*Y[g*ns+s,c]+sh), arg = first maximising s.
  * rsb_pool_backward_stats: dm = dOut masked by (pooled value > 0); stats[2C] += (sum dm, sum dm*xhat at the arg-max row).
  * rsb_bn_backward_coef: coefficients of dY = a*dZ + b*Y + d (BatchNorm backward) + dgamma/dbeta, from
- *   stats = (sum dZ, sum dZ*xhat [, second xhat when dual]). */
+ *   stats = (sum dZ, sum dZ*xhat [, second xhat when dual]); bit 1 of `dual` marks a BatchNorm that normalised with
+ *   its running statistics (eval mode / frozen): then dY = sc*dZ (b = d = 0), dgamma/dbeta unchanged.
+ * rsb_bn_eval_coef: sc/sh/mu/inv of an eval-mode BatchNorm from its running statistics (gamma/beta may be NULL). */
+int rsb_bn_eval_coef(int C, const float *gamma, const float *beta, const float *running_mean, const float *running_var,
+                     float eps, float *sc, float *sh, float *mu, float *inv, cudaStream_t stream);
 int rsb_bn_finalize(int C, long rows, const double *stats, const float *gamma, const float *beta, float eps,
                     float momentum, float *running_mean, float *running_var, float *sc, float *sh, float *mu,
                     float *inv, cudaStream_t stream);

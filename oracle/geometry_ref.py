@@ -1,5 +1,6 @@
-"""Umbrella-surface geometry shared by the dense and packed module layers (pure tensor math,
-device-agnostic, forward-only: coordinates never carry gradient on the RepSurf path).
+"""TEST INFRASTRUCTURE (never imported by repsurf_b200): umbrella-surface geometry as vectorised tensor math,
+device-agnostic, forward-only.  Pinned to the unmodified reference's tensors by tests/test_oracle_cpu.py and used by the
+GPU tests as a checker of csrc/umbrella.cu and csrc/group.cu on inputs the golden files do not cover.
 
 Restates, for a whole umbrella at once, what the reference spreads over
   {classification,segmentation}/modules/polar_utils.py:10-31        (xyz2sphere)

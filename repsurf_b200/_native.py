@@ -36,7 +36,8 @@ _SIGS = {
     "rsb_furthestsampling_packed_bounded": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],
     "rsb_knnquery_grid": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _l],
-    "rsb_umbrella_features": [_l, _i, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_umbrella_features": [_l, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i],
+    "rsb_bn_eval_coef": [_i, _p, _p, _p, _p, _f, _p, _p, _p, _p],
     "rsb_bn_update_running": [_i, _l, _p, _p, _f, _p, _p, _p],
     "rsb_segment_minmax": [_i, _l, _p, _p, _p, _p],
     "rsb_umbrella_mlp_stats": [_l, _i, _i, _p, _p, _p, _p],
@@ -61,7 +62,7 @@ _SIGS = {
     "rsb_pool_bn_backward_dense": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
-                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation", "rsb_fps_set_generation"])
+                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation", "rsb_fps_set_generation", "rsb_knn_grid_set_counters"])
 
 
 def build(force=False):
@@ -92,6 +93,8 @@ def lib():
         L.rsb_linear_tc_weight_floats.argtypes = [_i, _i]
         L.rsb_knn_grid_workspace_bytes.restype = _l
         L.rsb_knn_grid_workspace_bytes.argtypes = [_i, _i]
+        L.rsb_knn_grid_set_counters.restype = None
+        L.rsb_knn_grid_set_counters.argtypes = [_p]
         L.rsb_fps_set_generation.restype = None
         L.rsb_fps_set_generation.argtypes = [_i]
         L.rsb_tc_set_generation.restype = None

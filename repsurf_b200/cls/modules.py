@@ -11,16 +11,15 @@ What differs from the reference implementation (results are the same):
   * FPS also emits the sampled coordinates (no separate gathering launch), no `.zero_()` pre-fills,
     no `torch.cuda.empty_cache()` after every op, no permute().contiguous() round trips of the
     grouped tensor: groups are built channel-first [B,C,m,ns] directly by the grouping kernel.
-  * umbrella geometry is one vectorised routine (repsurf_b200.geometry.umbrella_features).
+  * umbrella geometry is one kernel (csrc/umbrella.cu); every Conv/BatchNorm/ReLU runs on the tcgen05 row GEMMs
+    (repsurf_b200.tc), in training and in eval mode.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import pointops as P
-from ..seg import pointops as PP
-from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, group_rows, linear_rows, pack_rows, sa_mlp
+from .. import tc
+from ..mlp import group_rows, sa_mlp
 
 
 def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_normal, return_polar):
@@ -36,35 +35,29 @@ def _grouped_inputs(npoint, radius, nsample, center_cf, normal, feature, return_
     new_normal = P.gathering(normal.contiguous(), fps_idx)              # [B,Cn,m]
     idx = P.ballquery(radius, nsample, xyz, new_xyz)                    # [B,m,ns] local ids
     gidx = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N).view(B, 1, 1)).view(B * npoint, nsample)
-    R = B * npoint * nsample
-    if (feature is None or return_normal):
-        # one kernel builds the packed row matrix [rel xyz, polar | normal | feature]
-        rows, layout = group_rows(xyz.view(B * N, 3), new_xyz.view(B * npoint, 3), gidx,
-                                  normal.transpose(1, 2).reshape(B * N, -1),
-                                  feature.transpose(1, 2).reshape(B * N, -1) if feature is not None else None,
-                                  nsample, return_polar)
-        return new_xyz.transpose(1, 2).contiguous(), new_normal, rows, layout
-    rel = PP.grouping(xyz.view(B * N, 3), gidx) - new_xyz.view(B * npoint, 1, 3)       # [B*m,ns,3]
-    pos = torch.cat([rel, xyz2sphere(rel)], dim=-1) if return_polar else rel
-    feats = []
-    if feature is None or return_normal:
-        feats.append(PP.grouping(normal.transpose(1, 2).reshape(B * N, -1), gidx).view(R, -1))
-    if feature is not None:
-        feats.append(PP.grouping(feature.transpose(1, 2).reshape(B * N, -1), gidx).view(R, -1))
-    rows, p4, f = pack_rows(pos.reshape(R, -1), feats)
-    return new_xyz.transpose(1, 2).contiguous(), new_normal, rows, (p4, f)
+    # one kernel builds the packed row matrix [rel xyz, polar | normal | feature]
+    use_normal = feature is None or return_normal
+    rows, layout = group_rows(xyz.view(B * N, 3), new_xyz.view(B * npoint, 3), gidx,
+                              normal.transpose(1, 2).reshape(B * N, -1) if use_normal else None,
+                              feature.transpose(1, 2).reshape(B * N, -1) if feature is not None else None,
+                              nsample, return_polar)
+    return new_xyz.transpose(1, 2).contiguous(), new_normal, rows, layout
 
 
 def _all_inputs(center_cf, normal, feature, return_normal, return_polar):
     """group_all (reference sample_and_group_all, repsurface_utils.py:62-88): one group holding every point,
-    RAW coordinates (not centre-relative), new_center = new_normal = zeros[B,3,1].  -> rows [B*N, C]."""
+    RAW coordinates (not centre-relative), new_center = new_normal = zeros[B,3,1].  -> rows [B*N, C].
+    Same row builder as the grouped levels: the group of cloud b is rows b*N .. (b+1)*N-1 around a zero centre
+    (x - 0 is exact, so the rows are the raw coordinates and their polar form)."""
     B, _, N = center_cf.shape
-    new_center = torch.zeros(B, 3, 1, device=center_cf.device, dtype=center_cf.dtype)
-    xyz = center_cf.transpose(1, 2)
-    pos = torch.cat([xyz, xyz2sphere(xyz)], dim=-1) if return_polar else xyz
-    feats = ([normal.transpose(1, 2).reshape(B * N, -1)] if return_normal else []) + [feature.transpose(1, 2).reshape(B * N, -1)]
-    rows, p4, f = pack_rows(pos.reshape(B * N, -1), feats)
-    return new_center, new_center, rows, (p4, f)
+    dev = center_cf.device
+    new_center = torch.zeros(B, 3, 1, device=dev, dtype=center_cf.dtype)
+    xyz = center_cf.transpose(1, 2).contiguous().view(B * N, 3)
+    idx = torch.arange(B * N, device=dev, dtype=torch.int32)
+    rows, layout = group_rows(xyz, new_center.view(B, 3), idx,
+                              normal.transpose(1, 2).reshape(B * N, -1) if return_normal else None,
+                              feature.transpose(1, 2).reshape(B * N, -1), N, return_polar)
+    return new_center, new_center, rows, layout
 
 
 class SurfaceAbstractionCD(nn.Module):
@@ -136,16 +129,14 @@ class UmbrellaSurfaceConstructor(nn.Module):
             # one kernel: drop the query itself (:119), azimuth sort, triangles, normals, centroids, polar, NaN repair
             from .. import _native as _nat
             gidx = (idx + (torch.arange(B, device=idx.device, dtype=torch.int32) * N_pts).view(B, 1, 1)).contiguous()
-            feat = torch.empty(B, N_pts, self.k - 1, 10, device=center.device)
+            # triangle rows of pitch 12 floats: 9 or 10 descriptor channels + zero padding (16-byte aligned rows for TMA)
+            feat = torch.empty(B, N_pts, self.k - 1, 12, device=center.device)
             _nat.call("rsb_umbrella_features", B * N_pts, self.k, 1, 0, 0, xyz.view(B * N_pts, 3), gidx.view(B * N_pts, self.k),
-                   sign.expand(B, N_pts, 1).reshape(B * N_pts).contiguous(), feat)
-            if not self.return_dist:
-                feat = feat[..., :9]
-            G, C = feat.shape[2], feat.shape[3]
-            rows = feat.reshape(B * N * G, C)
-        x = F.relu(bn_rows(linear_rows(rows, self.mlps[0]), self.mlps[1]))
-        x = F.relu(bn_rows(linear_rows(x, self.mlps[3]), self.mlps[4]))
-        x = linear_rows(x, self.mlps[6]).view(B, N, G, -1)
+                      sign.expand(B, N_pts, 1).reshape(B * N_pts).contiguous(), feat, 10 if self.return_dist else 9, 12)
+            G = self.k - 1
+        x = tc.linear_bn(feat.view(B * N * G, 12), self.mlps[0], self.mlps[1], relu=True)
+        x = tc.linear_bn(x, self.mlps[3], self.mlps[4], relu=True)
+        x = tc.linear(x, self.mlps[6]).view(B, N, G, -1)
         if self.aggr_type == 'max':
             x = torch.max(x, 2)[0]
         elif self.aggr_type == 'avg':

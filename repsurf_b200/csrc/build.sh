@@ -10,8 +10,8 @@ mkdir -p obj
 pids=()
 for s in $SRCS; do
   o=obj/${s%.cu}.o
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ "${FORCE:-0}" = 1 ]; then
-    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$s" -o "$o" &
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ -n "$(find . -maxdepth 1 \( -name "*.cuh" -o -name "*.h" \) -newer "$o")" ] || [ "${FORCE:-0}" = 1 ]; then
+    $NVCC $FLAGS ${RSB_EXTRA_FLAGS:-} ${PTXAS_V:+-Xptxas -v} -c "$s" -o "$o" &
     pids+=($!)
   fi
 done

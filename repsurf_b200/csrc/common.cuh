@@ -66,6 +66,14 @@ __device__ __forceinline__ float rsb_sqdist(float ax, float ay, float az, float 
     return __fmaf_rn(dz, dz, t);
 }
 
+// ReLU that propagates NaN like torch.relu (fmaxf returns the non-NaN operand: a diverged activation would turn into 0)
+__device__ __forceinline__ float rsb_relu(float x)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ---- cluster / DSMEM primitives -------------------------------------------------------------
 __device__ __forceinline__ uint32_t rsb_cluster_ctarank()
 {

@@ -177,6 +177,7 @@ struct GridQuery {
     int *idx;
     float *dist2;
     int b, m_dense, m_total, k, packed, sqrt_out;
+    unsigned long long *counters;   // optional [3]: candidates evaluated, cell ranges scanned, tie replays (measurement only)
 };
 
 __device__ __forceinline__ bool lex_less_g(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
@@ -261,7 +262,10 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
     const int *cs = P.cell_start + g.cell_base;
     const int rmax = max(max(g.gx, g.gy), g.gz);
 
+    unsigned n_cand = 0, n_ranges = 0;
     auto scan_range = [&](int j0, int j1) {
+        n_cand += (unsigned)max(j1 - j0, 0);
+        n_ranges++;
         for (int base = j0; base < j1; base += 32) {
             const int j = base + lane;
             float d = CUDART_INF_F;
@@ -343,6 +347,11 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
         if (face > slack && kth_d < (face - slack) * (face - slack) * 0.9999f) break;
     }
 
+    if (P.counters && lane == 0) {
+        atomicAdd(P.counters, (unsigned long long)n_cand);
+        atomicAdd(P.counters + 1, (unsigned long long)n_ranges);
+        if (HEAP && tie) atomicAdd(P.counters + 2, 1ull);
+    }
     int *oi = P.idx + (size_t)qi * k;
     float *od = P.dist2 ? P.dist2 + (size_t)qi * k : nullptr;
     if (HEAP && tie) {
@@ -384,6 +393,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 // bytes of scratch needed by rsb_knnquery_grid for n_total candidate points in b segments
+// measurement hook (bench.py): device buffer of 3 x u64 that every grid search adds its work to (candidates evaluated, cell
+// ranges scanned, queries that went through the exact tie replay); NULL (default) disables the counting
+static unsigned long long *g_knn_counters = nullptr;
+RSB_EXPORT void rsb_knn_grid_set_counters(unsigned long long *dev_counters) { g_knn_counters = dev_counters; }
+
 RSB_EXPORT long rsb_knn_grid_workspace_bytes(int n_total, int b)
 {
     size_t bytes = 0;
@@ -431,5 +445,6 @@ RSB_EXPORT int rsb_knnquery_grid(int packed, int heap, int b, int n, int m, int 
     Q.xyz = xyz; Q.new_xyz = new_xyz; Q.new_offset = packed ? new_offset : nullptr; Q.seg = G.seg;
     Q.cell_start = G.cell_cnt; Q.sorted = G.sorted; Q.idx = idx; Q.dist2 = dist;
     Q.b = b; Q.m_dense = m; Q.m_total = m_total; Q.k = nsample; Q.packed = packed; Q.sqrt_out = sqrt_out;
+    Q.counters = g_knn_counters;
     return heap ? launch_query<true>(Q, stream) : launch_query<false>(Q, stream);
 }

@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(long G, int ns, int C, co
         float best = -1.f;
         int bi = 0;
         for (int s = 0; s < ns; s++) {
-            const float z = fmaxf(fmaf(__ldg(y + (size_t)s * ldy), a, b), 0.f);
-            if (z > best) { best = z; bi = s; }
+            const float z = rsb_relu(fmaf(__ldg(y + (size_t)s * ldy), a, b));
+            if (z > best || (z != z && best == best)) { best = z; bi = s; }      // the first NaN wins and stays (torch.max propagates it)
         }
         out[i] = best;
         arg[i] = bi;
@@ -101,7 +101,23 @@ __global__ void __launch_bounds__(256) pool_bwd_stats_kernel(long G, int ns, int
 // BatchNorm backward as an affine map of stored tensors: dY = a*dZ + b*Y + d, with
 //   m1 = mean(dZ), m2 = mean(dZ*xhat):  a = sc, b = -sc*m2*inv, d = sc*(m2*mu*inv - m1);  dgamma = sum dZ*xhat, dbeta = sum dZ.
 // dual: two BatchNorms share dZ (stats = [sum dZ | sum dZ*xhat_1 | sum dZ*xhat_2]); outputs have 2C entries.
-__global__ void bn_bwd_coef_kernel(int C, double rows, const double *__restrict__ stats, int dual,
+// sc = gamma / sqrt(running_var + eps), sh = beta - running_mean * sc, mu = running_mean, inv = 1 / sqrt(running_var + eps):
+// the coefficient vectors of an eval-mode (or frozen) BatchNorm, in the form the GEMM operand transforms take
+__global__ void bn_eval_coef_kernel(int C, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                    const float *__restrict__ rm, const float *__restrict__ rv, float eps,
+                                    float *__restrict__ sc, float *__restrict__ sh, float *__restrict__ mu, float *__restrict__ inv)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double istd = 1.0 / sqrt((double)rv[c] + (double)eps);
+    const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+    sc[c] = (float)(g * istd);
+    sh[c] = (float)(b - (double)rm[c] * g * istd);
+    mu[c] = rm[c];
+    inv[c] = (float)istd;
+}
+
+__global__ void bn_bwd_coef_kernel(int C, double rows, const double *__restrict__ stats, int dual, int frozen,
                                    const float *__restrict__ sc, const float *__restrict__ mu,
                                    const float *__restrict__ inv, float *__restrict__ a, float *__restrict__ b,
                                    float *__restrict__ d, float *__restrict__ dgamma_over_g, float *__restrict__ dbeta)
@@ -113,8 +129,9 @@ __global__ void bn_bwd_coef_kernel(int C, double rows, const double *__restrict_
         const double m1 = s1 / rows, m2 = s2 / rows;
         const double scale = sc[i], mean = mu[i], istd = inv[i];
         a[i] = (float)scale;
-        b[i] = (float)(-scale * m2 * istd);
-        d[i] = (float)(scale * (m2 * mean * istd - m1));
+        // frozen BatchNorm (running statistics): the statistics are constants, dY = scale * dZ
+        b[i] = frozen ? 0.f : (float)(-scale * m2 * istd);
+        d[i] = frozen ? 0.f : (float)(scale * (m2 * mean * istd - m1));
         dgamma_over_g[i] = (float)s2;     // d(loss)/d(gamma)
         dbeta[i] = (float)s1;             // d(loss)/d(beta)
     }
@@ -193,7 +210,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(long rows, int C, const f
         const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + (size_t)r * ldy + c));
         const float4 a = __ldg(reinterpret_cast<const float4 *>(sc + c)), b = __ldg(reinterpret_cast<const float4 *>(sh + c));
         float4 o = make_float4(fmaf(y.x, a.x, b.x), fmaf(y.y, a.y, b.y), fmaf(y.z, a.z, b.z), fmaf(y.w, a.w, b.w));
-        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (relu) { o.x = rsb_relu(o.x); o.y = rsb_relu(o.y); o.z = rsb_relu(o.z); o.w = rsb_relu(o.w); }
         *reinterpret_cast<float4 *>(out + (size_t)r * ldo + c) = o;
     }
 }
@@ -323,9 +340,21 @@ RSB_EXPORT int rsb_bn_backward_coef(int C, long rows, const double *stats, int d
                                     cudaStream_t stream)
 {
     RSB_REQUIRE(C >= 1 && rows >= 1, "bad sizes");
-    bn_bwd_coef_kernel<<<RSB_DIVUP(dual ? 2 * C : C, 128), 128, 0, stream>>>(C, (double)rows, stats, dual, sc, mu, inv, a,
+    const int frozen = (dual >> 1) & 1;     // bit 1 of `dual`: running-statistics BatchNorm
+    dual &= 1;
+    bn_bwd_coef_kernel<<<RSB_DIVUP(dual ? 2 * C : C, 128), 128, 0, stream>>>(C, (double)rows, stats, dual, frozen, sc, mu, inv, a,
                                                                             b, d, dgamma, dbeta);
     RSB_CHECK_LAUNCH("bn_bwd_coef_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+RSB_EXPORT int rsb_bn_eval_coef(int C, const float *gamma, const float *beta, const float *running_mean, const float *running_var,
+                                float eps, float *sc, float *sh, float *mu, float *inv, cudaStream_t stream)
+{
+    RSB_REQUIRE(C >= 1 && running_mean && running_var && sc && sh && mu && inv, "bad arguments");
+    bn_eval_coef_kernel<<<RSB_DIVUP(C, 128), 128, 0, stream>>>(C, gamma, beta, running_mean, running_var, eps, sc, sh, mu, inv);
+    RSB_CHECK_LAUNCH("bn_eval_coef_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;
 }

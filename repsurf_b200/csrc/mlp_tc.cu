@@ -226,11 +226,11 @@ __device__ __forceinline__ void opnd_apply4(const Opnd &O, const Coef4 &c, const
         break;
     case RSB_OPND_BN_RELU:
 #pragma unroll
-        for (int e = 0; e < 4; e++) v[e] = fmaxf(fmaf(u[e], c.a[e], c.d[e]), 0.f);
+        for (int e = 0; e < 4; e++) v[e] = rsb_relu(fmaf(u[e], c.a[e], c.d[e]));
         break;
     case RSB_OPND_DUAL_BN_RELU:
 #pragma unroll
-        for (int e = 0; e < 4; e++) v[e] = fmaxf(fmaf(u[e], c.a[e], c.d[e]) + fmaf(w[e], c.a2[e], c.d2[e]), 0.f);
+        for (int e = 0; e < 4; e++) v[e] = rsb_relu(fmaf(u[e], c.a[e], c.d[e]) + fmaf(w[e], c.a2[e], c.d2[e]));
         break;
     case RSB_OPND_AFFINE2:
 #pragma unroll
@@ -291,7 +291,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void split4(const float *v, float4 &hi, float4 &lo)
 {
     hi.x = to_tf32(v[0]); hi.y = to_tf32(v[1]); hi.z = to_tf32(v[2]); hi.w = to_tf32(v[3]);
-    lo.x = to_tf32(v[0] - hi.x); lo.y = to_tf32(v[1] - hi.y); lo.z = to_tf32(v[2] - hi.z); lo.w = to_tf32(v[3] - hi.w);
+    // the residual goes to the tensor core unrounded (kind::tf32 truncates it; NaN survives): see tc_common.cuh split4
+    lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
 }
 
 // column sums of a warp's 32x32 register tile through a padded shared tile; result for column `lane`
@@ -861,8 +862,8 @@ __device__ __forceinline__ void wunit_store(const WUnit &U, const Opnd &O, long 
             if (r0 + e >= rows) continue;
             switch (O.kind) {
             case RSB_OPND_RAW: v[e] = U.u[e]; break;
-            case RSB_OPND_BN_RELU: v[e] = fmaxf(fmaf(U.u[e], U.a, U.d), 0.f); break;
-            case RSB_OPND_DUAL_BN_RELU: v[e] = fmaxf(fmaf(U.u[e], U.a, U.d) + fmaf(U.w[e], U.a2, U.d2), 0.f); break;
+            case RSB_OPND_BN_RELU: v[e] = rsb_relu(fmaf(U.u[e], U.a, U.d)); break;
+            case RSB_OPND_DUAL_BN_RELU: v[e] = rsb_relu(fmaf(U.u[e], U.a, U.d) + fmaf(U.w[e], U.a2, U.d2)); break;
             case RSB_OPND_AFFINE2: v[e] = fmaf(U.a, U.u[e], fmaf(U.b, U.w[e], U.d)); break;
             default: v[e] = fmaf(U.a, __float_as_int(U.u[e]) ? U.dz[e] : 0.f, fmaf(U.b, U.w[e], U.d)); break;
             }
@@ -993,8 +994,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wgrad_kernel(const __grid_con
                             const float w = rb.quads ? pb[(size_t)e * rb.quads * 4] : 0.f;
                             switch (O.kind) {
                             case RSB_OPND_RAW: v[e] = u; break;
-                            case RSB_OPND_BN_RELU: v[e] = fmaxf(fmaf(u, a, d), 0.f); break;
-                            case RSB_OPND_DUAL_BN_RELU: v[e] = fmaxf(fmaf(u, a, d) + fmaf(w, a2, d2), 0.f); break;
+                            case RSB_OPND_BN_RELU: v[e] = rsb_relu(fmaf(u, a, d)); break;
+                            case RSB_OPND_DUAL_BN_RELU: v[e] = rsb_relu(fmaf(u, a, d) + fmaf(w, a2, d2)); break;
                             default: v[e] = fmaf(a, u, fmaf(b, w, d)); break;
                             }
                             if (e >= lim) v[e] = 0.f;
@@ -1214,6 +1215,10 @@ RSB_EXPORT int rsb_linear_tc_prep_weight(int N, int K, const float *W, int ldw, 
     return 0;
 }
 
+// RSB_TC_TRACE=1: report every launch that falls back to the first-generation (SIMT-staged) kernels
+static const int g_tc_sync = getenv("RSB_TC_SYNC") ? 1 : 0;
+static const int g_tc_trace = [] { const char *v = getenv("RSB_TC_TRACE"); return (v && v[0] && v[0] != '0') ? 1 : 0; }();
+
 RSB_EXPORT int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float *Wp, const rsb_epi_t *E,
                              cudaStream_t stream)
 {
@@ -1224,6 +1229,9 @@ RSB_EXPORT int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float 
     {   // TMA-fed kernel (mlp_tc2.cu) whenever the operands meet its alignment rules
         const int r2 = rsb_gemm_rows2_launch(rows, N, A, Wp, E, stream);
         if (r2 >= 0) return r2;
+        if (g_tc_trace)
+            fprintf(stderr, "[rsb] gemm_rows -> first-generation kernel: rows %ld N %d K %d kind %d k0 %d ku %d ldu %d ldv %d ldy %d epi %d\n", rows, N,
+                    A->K, A->kind, A->k0, A->ku, A->ldu, A->ldv, E->ldy, E->kind);
     }
     RowsParams P;
     P.A = *A; P.E = *E; P.Wp = Wp; P.rows = rows; P.N = N;
@@ -1240,7 +1248,7 @@ RSB_EXPORT int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float 
     const size_t ring_b = 2 * 4 * (size_t)PROD_THREADS * 16;      // one ring slot: 2 pieces x 4 rows x 256 threads x 16 B
     P.raw_depth = 0;
     P.stages = (int)(budget / stage_b);
-    if (al_u && al_v && !getenv("RSB_TC_SYNC")) {
+    if (al_u && al_v && !g_tc_sync) {
         for (int rd = 3; rd >= 2 && P.raw_depth == 0; rd--)
             if (budget >= 2 * stage_b + rd * ring_b) { P.raw_depth = rd; P.stages = (int)((budget - rd * ring_b) / stage_b); }
     }
@@ -1269,6 +1277,9 @@ RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *
     {
         const int r2 = rsb_gemm_wgrad2_launch(rows, G, X, dW, ldw, stream);
         if (r2 >= 0) return r2;
+        if (g_tc_trace)
+            fprintf(stderr, "[rsb] gemm_wgrad -> first-generation kernel: rows %ld G(K %d kind %d k0 %d ku %d ldu %d ldv %d) X(K %d kind %d k0 %d ku %d ldu %d ldv %d)\n",
+                    rows, G->K, G->kind, G->k0, G->ku, G->ldu, G->ldv, X->K, X->kind, X->k0, X->ku, X->ldu, X->ldv);
     }
     WgradParams P;
     P.G = *G; P.X = *X; P.dW = dW; P.ldw = ldw; P.rows = rows;
@@ -1310,7 +1321,7 @@ RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *
     P.raw_slots = 0;
     P.raw_slot_bytes = 0;
     P.stages = (int)(budget / stage_b);
-    if (aligned(G) && aligned(X) && !getenv("RSB_TC_SYNC")) {
+    if (aligned(G) && aligned(X) && !g_tc_sync) {
         const size_t slot = (size_t)KC * 16 * max_quads;
         // two operand stages are enough once loads are decoupled; spend the rest of shared memory on ring depth
         if (budget >= 2 * stage_b + 3 * slot) {

@@ -139,18 +139,23 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v)
 
 // round-to-nearest (ties away) to tf32 for finite inputs: add half a tf32 ulp to the magnitude, clear 13 mantissa bits
 __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
-// a = hi + lo with hi = tf32(a), lo = tf32(a - hi): the 3xTF32 split
+// a = hi + lo with hi = tf32(a) (rounded) and lo = a - hi: the 3xTF32 split.  The residual is handed to the tensor core as
+// a plain fp32 value: kind::tf32 reads the upper 19 bits of its operands, i.e. truncates lo to tf32 itself (representation
+// error <= 2^-22 |a|, against 2^-23 with an explicit rounding that costs two more integer instructions per element).
+// NaN: to_tf32 maps the canonical NaN 0x7fffffff to -0, but lo = NaN - hi stays NaN, so a diverged activation still
+// reaches the accumulator as NaN (torch semantics).  -DRSB_LO_RAW=0 restores the explicit rounding of lo.
+#ifndef RSB_LO_RAW
+#define RSB_LO_RAW 1
+#endif
 __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo)
 {
     hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+#if RSB_LO_RAW
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+#else
     lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+#endif
 }
-// ReLU that propagates NaN like torch.relu (fmaxf would turn NaN into 0)
-__device__ __forceinline__ float relu_nan(float x)
-{
-    float r;
-    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
-    return r;
-}
+__device__ __forceinline__ float relu_nan(float x) { return rsb_relu(x); }
 
 }  // namespace rsbtc

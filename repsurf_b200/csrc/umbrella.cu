@@ -27,7 +27,8 @@ __device__ __forceinline__ float azimuth01(float y, float x) { return atan2f(y, 
 
 __global__ void __launch_bounds__(128) umbrella_kernel(long np, int k, int skip_first, int rotate, int order_seg,
                                                         const float *__restrict__ xyz, const int *__restrict__ idx,
-                                                        const float *__restrict__ flip, float *__restrict__ out)
+                                                        const float *__restrict__ flip, float *__restrict__ out, int channels,
+                                                        int ld)
 {
     const long p = blockIdx.x * 128L + threadIdx.x;
     if (p >= np) return;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(128) umbrella_kernel(long np, int k, int skip_
         ord[j + 1] = oi;
     }
     const float fl = flip ? flip[p] : 1.f;
-    float *o = out + (size_t)p * G * 10;
+    float *o = out + (size_t)p * G * ld;      // triangle rows of pitch ld (>= 10)
     float sign = 0.f;
     int first_ok = -1;
     // pass 1: raw descriptors; remember the first triangle whose normal is finite
@@ -78,34 +79,37 @@ __global__ void __launch_bounds__(128) umbrella_kernel(long np, int k, int skip_
         const float pos = (nx * mx + ny * my + nz * mz) / 1.7320508075688772f;
         const bool bad = isnan(nx) || isnan(ny) || isnan(nz);
         if (!bad && first_ok < 0) first_ok = i;
-        float *t = o + i * 10;
+        float *t = o + i * ld;
         if (order_seg) { t[0] = rho; t[1] = theta; t[2] = phi; t[3] = nx; t[4] = ny; t[5] = nz; t[6] = pos; t[7] = mx; t[8] = my; t[9] = mz; }
         else { t[0] = mx; t[1] = my; t[2] = mz; t[3] = rho; t[4] = theta; t[5] = phi; t[6] = nx; t[7] = ny; t[8] = nz; t[9] = pos; }
     }
     if (first_ok < 0) first_ok = 0;   // argmax over an all-false mask is 0 in the reference
     // pass 2: NaN repair (normal, centroid, pos of degenerate triangles <- first valid triangle); polar untouched
     const int no = order_seg ? 3 : 6, co = order_seg ? 7 : 0, po = order_seg ? 6 : 9;
-    const float *f = o + first_ok * 10;
+    const float *f = o + first_ok * ld;
     const float fn0 = f[no], fn1 = f[no + 1], fn2 = f[no + 2], fc0 = f[co], fc1 = f[co + 1], fc2 = f[co + 2], fp = f[po];
     for (int i = 0; i < G; i++) {
-        float *t = o + i * 10;
+        float *t = o + i * ld;
         if (isnan(t[no]) || isnan(t[no + 1]) || isnan(t[no + 2])) {
             t[no] = fn0; t[no + 1] = fn1; t[no + 2] = fn2;
             t[co] = fc0; t[co + 1] = fc1; t[co + 2] = fc2;
             t[po] = fp;
         }
+        for (int c = channels; c < ld; c++) t[c] = 0.f;    // dropped channel (return_dist=False) and alignment padding
     }
 }
 
 }  // namespace
 
-// xyz [rows,3]; idx [np,k] global row ids; flip [np] (+1/-1) or NULL; out [np, G, 10], G = k - (skip_first ? 1 : 0).
+// xyz [rows,3]; idx [np,k] global row ids; flip [np] (+1/-1) or NULL; out [np, G, ld], G = k - (skip_first ? 1 : 0):
+// the first `channels` (9 or 10) descriptor channels of every triangle, columns channels..ld-1 zero.
 RSB_EXPORT int rsb_umbrella_features(long np, int k, int skip_first, int rotate_key, int order_seg, const float *xyz,
-                                     const int *idx, const float *flip, float *out, cudaStream_t stream)
+                                     const int *idx, const float *flip, float *out, int channels, int ld, cudaStream_t stream)
 {
     RSB_REQUIRE(k >= 2 && k - (skip_first ? 1 : 0) <= MAXG, "group size out of range");
+    RSB_REQUIRE((channels == 9 || channels == 10) && ld >= 10, "channels must be 9 or 10 and ld >= 10");
     if (np == 0) return 0;
-    umbrella_kernel<<<(unsigned)((np + 127) / 128), 128, 0, stream>>>(np, k, skip_first, rotate_key, order_seg, xyz, idx, flip, out);
+    umbrella_kernel<<<(unsigned)((np + 127) / 128), 128, 0, stream>>>(np, k, skip_first, rotate_key, order_seg, xyz, idx, flip, out, channels, ld);
     RSB_CHECK_LAUNCH("umbrella_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;

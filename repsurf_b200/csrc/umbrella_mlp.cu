@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(UTPB) umb_forward_kernel(long rows, int g, con
             load_row(X, r, x);
             layer1(S, x, y);
 #pragma unroll
-            for (int c = 0; c < UC; c++) y[c] = fmaxf(fmaf(S.sc[c], y[c], S.sh[c]), 0.f);
+            for (int c = 0; c < UC; c++) y[c] = rsb_relu(fmaf(S.sc[c], y[c], S.sh[c]));
 #pragma unroll
             for (int c = 0; c < UC; c++) {
                 float a = S.b2[c];
@@ -157,7 +157,7 @@ __device__ __forceinline__ void backward_row(const UmbW &S, const float (&x)[UC]
     for (int k = 0; k < UC; k++) {
         xh[k] = (y[k] - S.mu[k]) * S.inv[k];
         const float z = fmaf(S.sc[k], y[k], S.sh[k]);
-        h[k] = fmaxf(z, 0.f);
+        h[k] = rsb_relu(z);
         float d = 0.f;
 #pragma unroll
         for (int c = 0; c < UC; c++) d = fmaf(S.w2[c][k], dO[c], d);

@@ -53,7 +53,12 @@ class RepSurfCls(nn.Module):
         center, normal, feature = self.sa1(center, normal, None)
         center, normal, feature = self.sa2(center, normal, feature)
         center, normal, feature = self.sa3(center, normal, feature)
-        return F.log_softmax(self.classfier(feature.view(-1, 1024)), -1)
+        # same head (Linear-BN-ReLU-Dropout x2, Linear), GEMMs + BatchNorm on the tensor cores
+        from . import tc
+        c = self.classfier
+        x = c[3](tc.linear_bn(feature.view(-1, 1024), c[0], c[1], relu=True))
+        x = c[7](tc.linear_bn(x, c[4], c[5], relu=True))
+        return F.log_softmax(tc.linear(x, c[8]), -1)
 
 
 class RepSurfSeg(nn.Module):
@@ -85,12 +90,10 @@ class RepSurfSeg(nn.Module):
         f2 = self.fp3([l2[0], l2[2], l2[3]], [l3[0], f3, l3[3]])
         f1 = self.fp2([l1[0], l1[2], l1[3]], [l2[0], f2, l2[3]])
         f0 = self.fp1([l0[0], None, l0[3]], [l1[0], f1, l1[3]])
-        if f0.is_cuda and self.training:
-            # same head (Linear-BN-ReLU-Dropout-Linear), GEMMs + BatchNorm on the tensor cores
-            from . import tc
-            c = self.classifier
-            return tc.linear(c[3](tc.linear_bn(f0, c[0], c[1], relu=True)), c[4])
-        return self.classifier(f0)
+        # same head (Linear-BN-ReLU-Dropout-Linear), GEMMs + BatchNorm on the tensor cores (training and eval)
+        from . import tc
+        c = self.classifier
+        return tc.linear(c[3](tc.linear_bn(f0, c[0], c[1], relu=True)), c[4])
 
 
 class SmoothClsLoss(nn.Module):

@@ -18,8 +18,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointops as P
-from ..geometry import umbrella_features, xyz2sphere
-from ..mlp import bn_rows, group_rows, linear_rows, pack_rows, sa_mlp
+from .. import _native as N
+from .. import tc
+from ..mlp import group_rows, sa_mlp
 
 
 def strided_offsets(offset, stride):
@@ -49,17 +50,8 @@ def _sample_and_group(stride, nsample, center, normal, feature, offset, return_p
     else:
         new_center, new_normal, new_offset = center, normal, offset
     group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
-    M = new_center.shape[0]
-    if center.is_cuda:
-        rows, layout = group_rows(center, new_center, group_idx, normal, feature, nsample, return_polar)
-        return new_center, new_normal, rows, layout, new_offset
-    rel = P.grouping(center, group_idx) - new_center.unsqueeze(1)
-    pos = torch.cat([rel, xyz2sphere(rel)], dim=-1) if return_polar else rel
-    feats = [P.grouping(normal.contiguous(), group_idx).view(M * nsample, -1)]
-    if feature is not None:
-        feats.append(P.grouping(feature.contiguous(), group_idx).view(M * nsample, -1))
-    rows, p4, f = pack_rows(pos.reshape(M * nsample, -1), feats)
-    return new_center, new_normal, rows, (p4, f), new_offset
+    rows, layout = group_rows(center, new_center, group_idx, normal, feature, nsample, return_polar)
+    return new_center, new_normal, rows, layout, new_offset
 
 
 class SurfaceAbstractionCD(nn.Module):
@@ -118,7 +110,6 @@ class SurfaceFeaturePropagationCD(nn.Module):
         xyz2, points2, offset2 = pos_feat_off2
         idx, dist = P.knnquery(3, xyz2, xyz1, offset2, offset1)             # coarse neighbours of every fine point
         weight = P._idw(dist).contiguous()
-        from .. import tc
         coarse = tc.linear_bn(points2, self.mlp_f0, self.norm_f0, relu=False)   # projected BEFORE interpolation (:267)
         x = P._InterpApply.apply(coarse, idx, weight)
         if self.skip:
@@ -154,28 +145,20 @@ class UmbrellaSurfaceConstructor(nn.Module):
                 keep = np.random.rand(offset.shape[0]) < 0.5
                 sizes = P._sizes(P.host_offsets(offset))
                 sign = torch.from_numpy(np.where(keep, 1.0, -1.0).astype(np.float32))
-                if center.is_cuda:
-                    sign = sign.pin_memory()
-                sign = sign.to(center.device, non_blocking=True)
+                sign = sign.pin_memory().to(center.device, non_blocking=True)
                 flip = torch.repeat_interleave(sign, P.const_tensor(sizes, torch.int64, center.device),
                                                output_size=center.shape[0])
             else:
                 flip = None
-            if center.is_cuda:
-                # one kernel: azimuth sort, triangles, normals, centroids, polar form, plane constant, NaN repair
-                from .. import _native as N
-                feat = torch.empty(center.shape[0], self.k, 10, device=center.device)
-                N.call("rsb_umbrella_features", center.shape[0], self.k, 0, 1 if self.sort == 'fix' else 0, 1,
-                       center.contiguous(), idx, flip, feat)
-            else:
-                offsets = center[idx.long()] - center.unsqueeze(1)
-                fl = flip.view(-1, 1, 1) if flip is not None else torch.ones(1, 1, 1)
-                feat = umbrella_features(offsets, fl, rotate_key=(self.sort == 'fix'), order="seg")
-            n, g, c = feat.shape
-            rows = feat.reshape(n * g, c)
-        if feat.is_cuda and c == 10 and self.mlps[0].weight.shape[0] == 10 and g <= 256:
+            # one kernel: azimuth sort, triangles, normals, centroids, polar form, plane constant, NaN repair
+            fused = self.mlps[0].weight.shape[0] == 10 and self.mlps[0].weight.shape[1] == 10 and self.k <= 256
+            ld = 10 if fused else 12                    # the generic path wants 16-byte aligned rows (TMA)
+            feat = torch.empty(center.shape[0], self.k, ld, device=center.device)
+            N.call("rsb_umbrella_features", center.shape[0], self.k, 0, 1 if self.sort == 'fix' else 0, 1,
+                   center.contiguous(), idx, flip, feat, 10, ld)
+        if fused:
             # both 10-channel layers, the BatchNorm, the ReLU and the sum over triangles in recomputing SIMT kernels
-            from ..tc import umbrella_mlp_fused
-            return umbrella_mlp_fused(feat, self.mlps[0], self.mlps[1], self.mlps[3])
-        x = F.relu(bn_rows(linear_rows(rows, self.mlps[0]), self.mlps[1]))
-        return linear_rows(x, self.mlps[3]).view(n, g, -1).sum(dim=1)
+            return tc.umbrella_mlp_fused(feat, self.mlps[0], self.mlps[1], self.mlps[3])
+        n, g, _ = feat.shape
+        x = tc.linear_bn(feat.view(n * g, ld), self.mlps[0], self.mlps[1], relu=True)
+        return tc.linear(x, self.mlps[3]).view(n, g, -1).sum(dim=1)

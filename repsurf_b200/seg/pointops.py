@@ -30,17 +30,18 @@ _HOST = {}
 
 
 def register_offsets(t, values):
-    """Remember the host values of an offset tensor created by this package (treated as immutable)."""
+    """Remember the host values of an offset tensor (keyed by identity AND in-place version: a later copy_() into the same
+    buffer invalidates the mirror, so static input buffers of a training loop are re-read, not trusted)."""
     key = id(t)
-    _HOST[key] = (weakref.ref(t, lambda _r, k=key: _HOST.pop(k, None)), tuple(int(v) for v in values))
+    _HOST[key] = (weakref.ref(t, lambda _r, k=key: _HOST.pop(k, None)), tuple(int(v) for v in values), t._version)
     return t
 
 
 def host_offsets(t):
     ent = _HOST.get(id(t))
-    if ent is not None and ent[0]() is t:
+    if ent is not None and ent[0]() is t and ent[2] == t._version:
         return ent[1]
-    vals = tuple(t.tolist())  # one D2H sync, only for offsets that came from outside
+    vals = tuple(t.tolist())  # one D2H sync, only for offsets that came from outside (or were modified in place)
     register_offsets(t, vals)
     return vals
 
@@ -65,6 +66,9 @@ def const_tensor(values, dtype, device):
 
 
 def make_offsets(values, device):
+    """Offset tensor for module outputs: a cached device constant (shared between calls with the same values; callers must
+    not write to it - an in-place edit bumps its version and is caught by host_offsets, but would still corrupt the other
+    holders of the constant)."""
     return register_offsets(const_tensor(values, torch.int32, device), values)
 
 

@@ -6,6 +6,7 @@ import ctypes
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import _native as N
 
@@ -88,15 +89,24 @@ def _bn_finalize(C, rows, stats, gamma, beta, eps, momentum, rm, rv, dev):
     return out[0], out[1], out[2], out[3]
 
 
-def _bn_eval_coef(bn_list):
-    """eval mode: scale/shift from the running statistics (tiny per-channel math)."""
-    g = torch.cat([b.weight for b in bn_list]).detach()
-    be = torch.cat([b.bias for b in bn_list]).detach()
-    rm = torch.cat([b.running_mean for b in bn_list])
-    rv = torch.cat([b.running_var for b in bn_list])
-    inv = torch.rsqrt(rv + bn_list[0].eps)
-    sc = g * inv
-    return sc.contiguous(), (be - rm * sc).contiguous(), rm.contiguous(), inv.contiguous()
+def _bn_eval_coef(bn_list, pad_to=None):
+    """Running-statistics BatchNorm(s) -> (sc, sh, mu, inv) rows of one [4, sum C] tensor (rsb_bn_eval_coef, one launch per
+    module).  pad_to: total width with trailing identity channels (sc = 1/sqrt(1+eps), sh = mu = 0)."""
+    dev = bn_list[0].running_mean.device
+    widths = [b.running_mean.shape[0] for b in bn_list]
+    total = sum(widths) if pad_to is None else pad_to
+    out = torch.zeros(4, total, dtype=torch.float32, device=dev) if total > sum(widths) else \
+        torch.empty(4, total, dtype=torch.float32, device=dev)
+    c0 = 0
+    for b, w in zip(bn_list, widths):
+        N.call("rsb_bn_eval_coef", w, None if b.weight is None else b.weight.detach(), None if b.bias is None else b.bias.detach(),
+               b.running_mean, b.running_var, float(b.eps), out[0, c0:c0 + w], out[1, c0:c0 + w], out[2, c0:c0 + w], out[3, c0:c0 + w])
+        c0 += w
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_uses_batch_stats(bn):
+    return bn.training or bn.running_mean is None
 
 
 class _FusedSAMLP(Function):
@@ -108,6 +118,8 @@ class _FusedSAMLP(Function):
     @staticmethod
     def forward(ctx, X, meta, *params):
         ns, P, eps, n_extra = meta["ns"], meta["pos_channel"], meta["eps"], meta["n_extra"]
+        frozen = meta["frozen"]          # BatchNorm layers normalise with their running statistics (eval / frozen)
+        bns = meta["bns"]
         dev = X.device
         R, Cin = X.shape
         G = R // ns
@@ -124,13 +136,19 @@ class _FusedSAMLP(Function):
         Y0 = torch.empty(R, 2 * C0, device=dev)
         # batch statistics of every layer: slices of ONE zeroed fp64 buffer (one fill launch per block)
         widths = [4 * C0] + [2 * params[8 + 4 * i].shape[0] for i in range(n_extra)]
-        stbuf = torch.zeros(sum(widths), dtype=torch.float64, device=dev)
-        stats_of = list(torch.split(stbuf, widths))
+        if frozen:
+            stats_of = [None] * (1 + n_extra)
+        else:
+            stbuf = torch.zeros(sum(widths), dtype=torch.float64, device=dev)
+            stats_of = list(torch.split(stbuf, widths))
         st = stats_of[0]
         gemm_rows(R, 2 * C0, opnd(OPND_RAW, X, Cin), Wp0, Y=Y0, bias=bias0, stats=st)
-        coefs = [_bn_finalize(2 * C0, R, st, torch.cat([g_l, g_f]).detach(), torch.cat([be_l, be_f]).detach(), eps, 0.0,
-                              None, None, dev)]
-        batch_stats = [st]
+        if frozen:
+            coefs = [_bn_eval_coef(bns[:2])]
+        else:
+            coefs = [_bn_finalize(2 * C0, R, st, torch.cat([g_l, g_f]).detach(), torch.cat([be_l, be_f]).detach(), eps, 0.0,
+                                  None, None, dev)]
+        batch_stats = [] if frozen else [st]
         Ys = [Y0]
         Ws = []
         prev = opnd(OPND_DUAL, Y0, C0, a=coefs[0][0], d=coefs[0][1], ku=C0)
@@ -143,9 +161,10 @@ class _FusedSAMLP(Function):
             Yi = torch.empty(R, Ci, device=dev)
             sti = stats_of[i + 1]
             gemm_rows(R, Ci, prev, Wp, Y=Yi, bias=b.detach(), stats=sti)
-            co = _bn_finalize(Ci, R, sti, g.detach(), be.detach(), eps, 0.0, None, None, dev)
+            co = _bn_eval_coef([bns[2 + i]]) if frozen else _bn_finalize(Ci, R, sti, g.detach(), be.detach(), eps, 0.0, None, None, dev)
             coefs.append(co)
-            batch_stats.append(sti)
+            if not frozen:
+                batch_stats.append(sti)
             Ys.append(Yi)
             Ws.append(W2)
             prev = opnd(OPND_BN_RELU, Yi, Ci, a=co[0], d=co[1])
@@ -155,13 +174,22 @@ class _FusedSAMLP(Function):
         N.call("rsb_pool_forward", G, ns, Cprev, Ys[-1], Ys[-1].stride(0), coefs[-1][0], coefs[-1][1], out, arg)
         ctx.meta = meta
         ctx.saved = (X, Wbd, Ws, Ys, coefs, arg)
+        ctx.consumed = False
         ctx.mark_non_differentiable(*batch_stats)
         return (out, *batch_stats)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dOut, *_unused):
         meta = ctx.meta
         ns, P, n_extra = meta["ns"], meta["pos_channel"], meta["n_extra"]
+        if ctx.consumed:
+            # the stored pre-BatchNorm activations are overwritten in place by dL/dY (rsb_pool_bn_backward_dense): a second
+            # backward through the same graph (retain_graph=True) would read gradients where it expects activations
+            raise RuntimeError("repsurf_b200 fused shared MLP: backward called twice on the same forward (its saved activations "
+                               "are consumed by the first backward); run the forward again instead of retain_graph=True")
+        ctx.consumed = True
+        fz = 2 if meta["frozen"] else 0
         X, Wbd, Ws, Ys, coefs, arg = ctx.saved
         dev = X.device
         R, Cin = X.shape
@@ -182,8 +210,9 @@ class _FusedSAMLP(Function):
         dm = torch.empty(G, CL, device=dev)
         N.call("rsb_pool_backward_stats", G, ns, CL, dOut.contiguous(), arg, Ys[L], Ys[L].stride(0), sc, sh, mu, inv, dm, st)
         co = torch.empty(5, CL, device=dev)
-        N.call("rsb_bn_backward_coef", CL, R, st, 0, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
+        N.call("rsb_bn_backward_coef", CL, R, st, fz, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
         grads[("g", L)], grads[("be", L)] = co[3], co[4]
+        scales = {L: sc}
         if L > 0 and CL % 4 == 0:
             # densify dL/dY_L in place of the stored Y_L (one streaming pass); the GEMMs then read a plain matrix
             N.call("rsb_pool_bn_backward_dense", G, ns, CL, dm, arg, Ys[L], Ys[L].stride(0), co[0], co[1], co[2])
@@ -213,8 +242,9 @@ class _FusedSAMLP(Function):
             gemm_rows(R, Cp, Gop, WpT, Y=dZ, stats=stp, mask=(Ys[l - 1], scp, shp, mup, invp, dual))
             width = 2 * Cp if dual else Cp
             cop = torch.empty(5, width, device=dev)
-            N.call("rsb_bn_backward_coef", Cp, R, stp, 1 if dual else 0, scp, mup, invp, cop[0], cop[1], cop[2], cop[3], cop[4])
+            N.call("rsb_bn_backward_coef", Cp, R, stp, (1 if dual else 0) | fz, scp, mup, invp, cop[0], cop[1], cop[2], cop[3], cop[4])
             grads[("g", l - 1)], grads[("be", l - 1)] = cop[3], cop[4]
+            scales[l - 1] = scp
             Gop = opnd(OPND_AFFINE2, dZ, width, a=cop[0], b=cop[1], d=cop[2], V=Ys[l - 1], ku=Cp)
             dZ0, cop0 = dZ, cop
         # ---- first layer: weight gradient of the block-diagonal GEMM, input gradient of the feature columns
@@ -238,11 +268,16 @@ class _FusedSAMLP(Function):
             z = zbuf[zpos[0]:zpos[0] + n]
             zpos[0] += n
             return z
+
+        def dbias(layer, lo, hi):
+            # frozen BatchNorm: dL/db = sum_r dY = sc * sum_r dZ  (per-channel vectors)
+            return (scales[layer][lo:hi] * grads[("be", layer)][lo:hi]) if fz else zero(hi - lo)
         out = [dX, None,
-               dWbd[:C0, :P].reshape(W_l_shape), zero(C0), dWbd[C0:, P4:P4 + F].reshape(W_f_shape), zero(C0),
+               dWbd[:C0, :P].reshape(W_l_shape), dbias(0, 0, C0), dWbd[C0:, P4:P4 + F].reshape(W_f_shape), dbias(0, C0, 2 * C0),
                grads[("g", 0)][:C0], grads[("be", 0)][:C0], grads[("g", 0)][C0:], grads[("be", 0)][C0:]]
         for i in range(n_extra):
-            out += [grads[("W", i + 1)].reshape(meta["W_shapes"][i]), zero(grads[("W", i + 1)].shape[0]),
+            Ci = grads[("W", i + 1)].shape[0]
+            out += [grads[("W", i + 1)].reshape(meta["W_shapes"][i]), dbias(i + 1, 0, Ci),
                     grads[("g", i + 1)], grads[("be", i + 1)]]
         return tuple(out)
 
@@ -257,20 +292,29 @@ def _update_running(bn, R, sums, sumsq):
 
 
 def sa_mlp_fused(rows, pos_channel, mod, nsample, layout=None):
-    """Drop-in for mlp.sa_mlp_rows on the tensor cores (training mode).  rows [G*nsample, C] -> [G, mlp[-1]].
-    layout = (first feature column, feature channels) when the row matrix carries alignment padding (mlp.pack_rows)."""
+    """Shared MLP + max-pool of a SurfaceAbstractionCD level on the tensor cores.  rows [G*nsample, C] -> [G, mlp[-1]].
+    layout = (first feature column, feature channels) of the packed row matrix (csrc/group.cu group_rows_fwd).
+    BatchNorm layers in training mode use batch statistics and update their running buffers; in eval mode (or frozen:
+    bn.eval() inside a training module) they normalise with the running statistics, as nn.BatchNorm does."""
     bns = [mod.bn_l0, mod.bn_f0] + list(mod.mlp_bns)
+    modes = {bn_uses_batch_stats(b) for b in bns}
+    if len(modes) != 1:
+        raise RuntimeError("repsurf_b200 fused shared MLP: the BatchNorm layers of one SurfaceAbstractionCD block must all be in "
+                           "the same mode (all training or all eval)")
+    frozen = not modes.pop()
     params = [mod.mlp_l0.weight, mod.mlp_l0.bias, mod.mlp_f0.weight, mod.mlp_f0.bias,
               mod.bn_l0.weight, mod.bn_l0.bias, mod.bn_f0.weight, mod.bn_f0.bias]
     for lin, bn in zip(mod.mlp_convs, mod.mlp_bns):
         params += [lin.weight, lin.bias, bn.weight, bn.bias]
     feat_col, feat_channels = layout if layout is not None else (pos_channel, rows.shape[1] - pos_channel)
     meta = dict(ns=nsample, pos_channel=pos_channel, feat_col=feat_col, feat_channels=feat_channels,
-                eps=mod.bn_l0.eps, n_extra=len(mod.mlp_convs),
+                eps=mod.bn_l0.eps, n_extra=len(mod.mlp_convs), frozen=frozen, bns=bns,
                 W_l_shape=tuple(mod.mlp_l0.weight.shape), W_f_shape=tuple(mod.mlp_f0.weight.shape),
                 W_shapes=[tuple(l.weight.shape) for l in mod.mlp_convs])
     res = _FusedSAMLP.apply(rows if rows.stride(1) == 1 else rows.contiguous(), meta, *params)
     out, stats = res[0], res[1:]
+    if frozen:
+        return out
     # running statistics (same side effects as the BatchNorm modules): batch mean, UNBIASED batch variance
     R = rows.shape[0]
     with torch.no_grad():
@@ -289,8 +333,11 @@ def sa_mlp_fused(rows, pos_channel, mod, nsample, layout=None):
 # Used by SurfaceFeaturePropagationCD, the umbrella MLP and the segmentation head.
 # ------------------------------------------------------------------------------------------------------------
 class _LinearBN(Function):
+    """out = [relu](bn(X W^T + b)) over rows.  `frozen` = (sc, sh, mu, inv) of a running-statistics BatchNorm, or None for
+    batch statistics (returned as the second output for the running-buffer update)."""
+
     @staticmethod
-    def forward(ctx, X, W, bias, gamma, beta, relu, eps):
+    def forward(ctx, X, W, bias, gamma, beta, relu, eps, frozen):
         dev = X.device
         X = X.contiguous()
         R, K = X.shape
@@ -298,19 +345,26 @@ class _LinearBN(Function):
         W2 = W.reshape(Nn, -1).detach().contiguous()
         Wp, _, _ = prep_weight(W2)
         Y = torch.empty(R, Nn, device=dev)
-        st = torch.zeros(2 * Nn, dtype=torch.float64, device=dev)
+        st = None if frozen is not None else torch.zeros(2 * Nn, dtype=torch.float64, device=dev)
         gemm_rows(R, Nn, opnd(OPND_RAW, X, K), Wp, Y=Y, bias=None if bias is None else bias.detach(), stats=st)
-        sc, sh, mu, inv = _bn_finalize(Nn, R, st, gamma.detach(), beta.detach(), eps, 0.0, None, None, dev)
+        if frozen is not None:
+            sc, sh, mu, inv = frozen
+        else:
+            sc, sh, mu, inv = _bn_finalize(Nn, R, st, gamma.detach(), beta.detach(), eps, 0.0, None, None, dev)
         out = torch.empty(R, Nn, device=dev)
         N.call("rsb_bn_apply", R, Nn, Y, Nn, sc, sh, 1 if relu else 0, out, Nn)
         ctx.relu = relu
         ctx.w_shape = tuple(W.shape)
         ctx.has_bias = bias is not None
+        ctx.frozen = frozen is not None
         ctx.saved = (X, W2, Y, sc, sh, mu, inv)
+        if st is None:
+            st = torch.empty(0, dtype=torch.float64, device=dev)
         ctx.mark_non_differentiable(st)
         return out, st
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dOut, _st):
         X, W2, Y, sc, sh, mu, inv = ctx.saved
         dev = X.device
@@ -324,7 +378,7 @@ class _LinearBN(Function):
             msc, msh = torch.zeros(Nn, device=dev), torch.ones(Nn, device=dev)
         N.call("rsb_bn_relu_backward", R, Nn, dZ, Nn, Y, Nn, msc, msh, mu, inv, 0, st)
         co = torch.empty(5, Nn, device=dev)
-        N.call("rsb_bn_backward_coef", Nn, R, st, 0, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
+        N.call("rsb_bn_backward_coef", Nn, R, st, 2 if ctx.frozen else 0, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
         G = opnd(OPND_AFFINE2, dZ, Nn, a=co[0], b=co[1], d=co[2], V=Y, ku=Nn)
         dW = torch.zeros(Nn, K, device=dev)
         gemm_wgrad(R, G, opnd(OPND_RAW, X, K), dW)
@@ -333,8 +387,10 @@ class _LinearBN(Function):
             WpT, _, _ = prep_weight(W2, transposed=True)
             dX = torch.empty(R, K, device=dev)
             gemm_rows(R, K, G, WpT, Y=dX)
-        db = torch.zeros(Nn, device=dev) if ctx.has_bias else None      # a bias in front of BatchNorm has zero gradient
-        return dX, dW.reshape(ctx.w_shape), db, co[3], co[4], None, None
+        db = None
+        if ctx.has_bias:   # a bias in front of a batch-statistics BatchNorm has zero gradient; frozen: sc * sum dZ
+            db = sc * co[4] if ctx.frozen else torch.zeros(Nn, device=dev)
+        return dX, dW.reshape(ctx.w_shape), db, co[3], co[4], None, None, None
 
 
 def _pad4(n):
@@ -343,7 +399,7 @@ def _pad4(n):
 
 class _Linear(Function):
     """Y = X W^T + b.  Output and incoming gradient live in row-padded buffers (pitch a multiple of 4 floats) so that
-    the narrow classifier head (13 classes) stays on the TMA-fed kernels; the caller sees a [R, N] view."""
+    narrow layers (13 classes, 10 umbrella channels) stay on the TMA-fed kernels; the caller sees a [R, N] view."""
 
     @staticmethod
     def forward(ctx, X, W, bias):
@@ -359,6 +415,7 @@ class _Linear(Function):
         return Ybuf[:, :Nn]
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dY):
         X, W2 = ctx.saved
         R, K = X.shape
@@ -377,27 +434,43 @@ class _Linear(Function):
         return dX, dW, (dY.sum(0) if ctx.has_bias else None)
 
 
+def _pad_vec(v, n, value=0.0):
+    return v if v is None or v.shape[0] == n else torch.nn.functional.pad(v, (0, n - v.shape[0]), value=value)
+
+
 def linear_bn(x, lin, bn, relu):
-    """[relu](bn(lin(x))) over rows.  Training mode on CUDA runs on the tensor cores; eval falls back to torch."""
-    if not (bn.training and x.is_cuda and lin.weight.shape[0] % 4 == 0):
-        w = lin.weight
-        y = torch.nn.functional.linear(x, w.view(w.shape[0], -1), lin.bias)
-        y = torch.nn.functional.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
-                                           0.0 if bn.momentum is None else bn.momentum, bn.eps)
-        if bn.training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
-        return torch.relu(y) if relu else y
-    out, st = _LinearBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, relu, bn.eps)
-    R, C = x.shape[0], lin.weight.shape[0]
-    with torch.no_grad():
-        _update_running(bn, R, st[:C], st[C:])
+    """[relu](bn(lin(x))) over rows [R, K'] on the tensor cores, K' >= in_features (extra input columns must be zero).
+    Channel counts that are not multiples of 4 (the 10-channel umbrella layers) run zero-padded to the next multiple:
+    the result then has pad4(out_features) columns, the padding columns exactly zero.  Train-mode BatchNorm uses batch
+    statistics and updates the running buffers; eval-mode (or frozen) BatchNorm uses the running statistics."""
+    if not x.is_cuda:
+        raise RuntimeError("repsurf_b200 has no CPU path")
+    W = lin.weight.reshape(lin.weight.shape[0], -1)
+    C, K = W.shape
+    Cp, Kp = _pad4(C), x.shape[1]
+    assert Kp >= K and Kp % 4 == 0, "input rows must be padded to a multiple of 4 channels"
+    if Cp != C or Kp != K:
+        W = torch.nn.functional.pad(W, (0, Kp - K, 0, Cp - C))
+    bias = _pad_vec(lin.bias, Cp)
+    gamma = _pad_vec(bn.weight if bn.weight is not None else torch.ones(C, device=x.device), Cp, 1.0)
+    beta = _pad_vec(bn.bias if bn.bias is not None else torch.zeros(C, device=x.device), Cp)
+    batch = bn_uses_batch_stats(bn)
+    frozen = None if batch else _bn_eval_coef([bn], pad_to=Cp)
+    out, st = _LinearBN.apply(x, W, bias, gamma, beta, relu, bn.eps, frozen)
+    if batch and bn.training:
+        with torch.no_grad():
+            _update_running(bn, x.shape[0], st[:C], st[Cp:Cp + C])
     return out
 
 
 def linear(x, lin):
+    """lin(x) over rows [R, K'], K' >= in_features with zero extra columns; -> [R, out_features] view."""
     if not x.is_cuda:
-        return torch.nn.functional.linear(x, lin.weight, lin.bias)
-    return _Linear.apply(x, lin.weight, lin.bias)
+        raise RuntimeError("repsurf_b200 has no CPU path")
+    W = lin.weight.reshape(lin.weight.shape[0], -1)
+    if x.shape[1] != W.shape[1]:
+        W = torch.nn.functional.pad(W, (0, x.shape[1] - W.shape[1]))
+    return _Linear.apply(x, W, lin.bias)
 
 
 class _UmbrellaMLP(Function):

@@ -365,10 +365,11 @@ def test_knn_grid_lattice_and_degenerate_inputs(monkeypatch):
 # ------------------------------------------------------------------------------------------- fused umbrella geometry
 @pytest.mark.parametrize("order,rotate,skip", [("seg", True, False), ("cls", False, True)])
 def test_umbrella_kernel_matches_tensor_formulation(order, rotate, skip):
-    """csrc/umbrella.cu vs repsurf_b200.geometry.umbrella_features (the vectorised restatement that the golden
-    model tests pin to the reference).  Points whose neighbour azimuths tie within an ulp may sort differently."""
+    """csrc/umbrella.cu vs oracle.geometry_ref.umbrella_features (a vectorised torch restatement, itself pinned to the
+    unmodified reference's tensors by tests/test_oracle_cpu.py; the kernel is pinned to them directly in
+    tests/test_models_gpu.py).  Points whose neighbour azimuths tie within an ulp may sort differently."""
     from repsurf_b200 import _native as N
-    from repsurf_b200.geometry import umbrella_features
+    from oracle.geometry_ref import umbrella_features
     P = _seg()
     g = torch.Generator().manual_seed(41)
     n, k = 6000, 9
@@ -378,7 +379,7 @@ def test_umbrella_kernel_matches_tensor_formulation(order, rotate, skip):
     flip = (torch.randint(0, 2, (n,), generator=g).float() * 2 - 1).to(cuda)
     G = k - (1 if skip else 0)
     out = torch.empty(n, G, 10, device=cuda)
-    N.call("rsb_umbrella_features", n, k, 1 if skip else 0, 1 if rotate else 0, 1 if order == "seg" else 0, xyz, idx, flip, out)
+    N.call("rsb_umbrella_features", n, k, 1 if skip else 0, 1 if rotate else 0, 1 if order == "seg" else 0, xyz, idx, flip, out, 10, 10)
     nb = idx[:, 1:] if skip else idx
     offsets = xyz[nb.long()] - xyz[:, None]
     want = umbrella_features(offsets, flip.view(-1, 1, 1), rotate_key=rotate, order=order)
@@ -393,7 +394,7 @@ def test_group_rows_matches_gather_composition(polar, cf):
     """csrc/group.cu group_rows_* vs the reference's composition (gathers, subtraction, xyz2sphere, cat:
     segmentation/modules/repsurface_utils.py:36-49): gathers and relative xyz bit-exact, polar columns to an ulp of
     the libdevice functions, backward scatter against an fp64 index_add."""
-    from repsurf_b200.geometry import xyz2sphere
+    from oracle.geometry_ref import xyz2sphere
     from repsurf_b200.mlp import group_rows
     g = torch.Generator().manual_seed(43)
     n, M, ns, cn = 5000, 700, 24, 10

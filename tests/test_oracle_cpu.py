@@ -170,3 +170,52 @@ def test_model_ref_seg_matches_reference_golden(golden_dir):
     sd = model.state_dict()
     assert _close(sd["sa1.bn_l0.running_mean"].numpy(), g["bn_mean"])[0]
     assert _close(sd["fp2.norm_s0.running_var"].numpy(), g["bn_var"])[0]
+
+
+def test_model_ref_state_dict_keys_match_reference(golden_dir):
+    """The oracle's model restatement, like the CUDA models, must carry the reference's exact state_dict keys / shapes."""
+    import json
+    ref = json.load(open(os.path.join(golden_dir, "reference_state_dict_keys.json")))
+    for mine, name in ((MR.ClsNet(), "cls"), (MR.SegNet(), "seg")):
+        assert {k: list(v.shape) for k, v in mine.state_dict().items()} == ref[name]
+
+
+def test_model_ref_eval_mode_matches_reference_golden(golden_dir):
+    e = np.load(os.path.join(golden_dir, "eval_mode.npz"))
+    g = np.load(os.path.join(golden_dir, "seg_10240_6000.npz"))
+    model = MR.det_fill_(MR.SegNet()).eval()
+    taps = {}
+    np.random.seed(4321)
+    with torch.no_grad():
+        out = model([torch.from_numpy(g["coord"]), torch.from_numpy(g["feat"]), torch.from_numpy(g["offset"])], taps)
+    assert np.array_equal(taps["sa1_center"].numpy(), e["seg_sa1_center"])      # plain FPS in eval mode: exact
+    for name, got in (("seg_sa1_feat", taps["sa1_feat"][::4]), ("seg_out", out[::8])):
+        ok, err = _close(got.numpy(), e[name])
+        assert ok, (name, err)
+    gc = np.load(os.path.join(golden_dir, "cls_b6_n1024.npz"))
+    model = MR.det_fill_(MR.ClsNet()).eval()
+    taps = {}
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        out = model(torch.from_numpy(gc["x"]), taps)
+    for name, got in (("cls_sa3_feat", taps["sa3_feat"]), ("cls_out", out)):
+        ok, err = _close(got.numpy(), e[name])
+        assert ok, (name, err)
+
+
+def test_geometry_ref_umbrella_matches_reference_tensors(golden_dir):
+    """oracle/geometry_ref.py (vectorised umbrella restatement used as a checker by the GPU tests) against the umbrella
+    descriptors of the UNMODIFIED reference (input of its umbrella MLP), same kNN lists from the C oracle."""
+    from oracle import oracle as O
+    from oracle.geometry_ref import umbrella_features
+    g = np.load(os.path.join(golden_dir, "seg_10240_6000.npz"))
+    coord, offset = torch.from_numpy(g["coord"]), torch.from_numpy(g["offset"])
+    idx, _ = O.knn_packed(9, coord, coord, offset, offset)
+    np.random.seed(4321)
+    keep = np.random.rand(offset.shape[0]) < 0.5
+    sizes = np.diff(np.concatenate([[0], g["offset"]]))
+    flip = torch.from_numpy(np.repeat(np.where(keep, 1.0, -1.0).astype(np.float32), sizes))
+    sel = torch.arange(0, coord.shape[0], 8)
+    offs = coord[idx[sel].long()] - coord[sel][:, None]
+    got = umbrella_features(offs, flip[sel].view(-1, 1, 1), rotate_key=True, order="seg").numpy()
+    assert np.abs(got - g["umb_feat"]).max() < 1e-6
