@@ -429,6 +429,11 @@ def build_rooflines(per_entry, knn_work, ms_step, steps, workload):
                                    "launch_ms": t_ms, "launch": k[1] + f" (lowest fraction among shapes with >= 2 % of the GEMM time; "
                                    f"{round(100 * d['ms'] / gemm_ms, 1)} % of it)", "algorithmic_bytes_per_launch": d["bytes"]}
 
+    if shapes:
+        top = sorted(shapes.items(), key=lambda kd: -kd[1]["ms"])[:12]
+        rooflines["gemm_total"]["shapes_by_time"] = [
+            {"launch": k[1], "entry": k[0], "launches_per_step": d["n"] / steps, "ms_per_step": round(d["ms"] / steps, 4),
+             "frac": round(d["bytes"] * d["n"] / (d["ms"] * 1e-3) / 1e9 / hbm_peak, 3)} for k, d in top]
     for name, v in per_entry.items():
         if name.startswith("rsb_furthestsampling"):
             a, t_ms = biggest(v)

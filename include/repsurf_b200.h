@@ -109,6 +109,18 @@ int rsb_furthestsampling_packed_bounded(int b, int n_expect, int n_limit, const 
                                         const int *offset, const int *new_offset, float *tmp, int *idx, float *new_xyz,
                                         cudaStream_t stream);
 
+/* The sector split of sectorized_fps (seg/po/functions/pointops.py:61-93: per cloud angle = atan2(x, y), num_sectors
+ * equal-width sectors over [min, max + 1e-4], points of a sector in ascending index order) on the device, no host round trip.
+ * nsec [b] = sectors of each cloud (1 for clouds below min_points, else num_sectors), seg_first [b] = index of each cloud's
+ * first segment, nseg = sum(nsec) <= 512.  Outputs: order [n] = the stable segment-major permutation, sector_xyz [n,3] =
+ * xyz[order], sector_offset [nseg] = cumulative segment ends, count_max [1] = largest segment (may be NULL).
+ * rsb_sector_map_back: out[i] = order[idx[i]] as int64 (pointops.py:105). */
+long rsb_sector_split_workspace_bytes(int n, int b, int nseg);
+int rsb_sector_split(int b, int n, int num_sectors, int nseg, const float *xyz, const int *offset, const int *nsec,
+                     const int *seg_first, void *workspace, long workspace_bytes, int *order, float *sector_xyz,
+                     int *sector_offset, int *count_max, cudaStream_t stream);
+int rsb_sector_map_back(int m, const int *order, const int *idx, long long *out, cudaStream_t stream);
+
 /* replaces knnquery_cuda_launcher(m,nsample,xyz,new_xyz,offset,new_offset,idx,dist2)   seg/po/src/knnquery/knnquery_cuda_kernel.h:11
  * adds b (= number of clouds).  dist [m,nsample]: squared distances, or their square roots when sqrt_out != 0
  * (fuses the torch.sqrt of seg/po/functions/pointops.py:127).  1 <= nsample <= 100. */
@@ -151,11 +163,6 @@ int rsb_group_rows_forward(long rows, int ns, int polar, int P4, int Cn, int Cf,
                            cudaStream_t stream);
 int rsb_group_rows_backward(long rows, int P4, int Cn, int Cf, int ld, const float *drows, const int *idx, float *dnormal,
                             float *dfeature, cudaStream_t stream);
-
-/* per-segment min / max of packed values [n]; vmin / vmax [b] must be pre-set to +inf / -inf (exact, order-free).
- * Device replacement of the per-cloud .min()/.max() of the sector split, pointops.py:70-71. */
-int rsb_segment_minmax(int b, long n_max, const float *values, const int *offset, float *vmin, float *vmax,
-                       cudaStream_t stream);
 
 /* ------------------------------------------------------------------ umbrella surface descriptors (both layouts)
  * One kernel for group_by_umbrella[_v2] + cal_normal + cal_center + xyz2sphere + cal_const + check_nan_umb

@@ -34,12 +34,13 @@ _SIGS = {
     "rsb_interpolation_backward": [_i, _i, _i, _i, _p, _p, _p, _p],
     "rsb_furthestsampling_packed": [_i, _i, _p, _p, _p, _p, _p, _p, _p],
     "rsb_furthestsampling_packed_bounded": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "rsb_sector_split": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p],
+    "rsb_sector_map_back": [_i, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],
     "rsb_knnquery_grid": [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _l],
     "rsb_umbrella_features": [_l, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i],
     "rsb_bn_eval_coef": [_i, _p, _p, _p, _p, _f, _p, _p, _p, _p],
     "rsb_bn_update_running": [_i, _l, _p, _p, _f, _p, _p, _p],
-    "rsb_segment_minmax": [_i, _l, _p, _p, _p, _p],
     "rsb_umbrella_mlp_stats": [_l, _i, _i, _p, _p, _p, _p],
     "rsb_umbrella_mlp_forward": [_l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "rsb_umbrella_mlp_backward": [_l, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
@@ -62,7 +63,7 @@ _SIGS = {
     "rsb_pool_bn_backward_dense": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
-                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation", "rsb_fps_set_generation", "rsb_knn_grid_set_counters"])
+                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation", "rsb_fps_set_generation", "rsb_knn_grid_set_counters", "rsb_sector_split_workspace_bytes"])
 
 
 def build(force=False):
@@ -93,6 +94,8 @@ def lib():
         L.rsb_linear_tc_weight_floats.argtypes = [_i, _i]
         L.rsb_knn_grid_workspace_bytes.restype = _l
         L.rsb_knn_grid_workspace_bytes.argtypes = [_i, _i]
+        L.rsb_sector_split_workspace_bytes.restype = _l
+        L.rsb_sector_split_workspace_bytes.argtypes = [_i, _i, _i]
         L.rsb_knn_grid_set_counters.restype = None
         L.rsb_knn_grid_set_counters.argtypes = [_p]
         L.rsb_fps_set_generation.restype = None

@@ -219,40 +219,6 @@ __global__ void __launch_bounds__(TPB) group_rows_bwd(long rows, int P4, int Cn,
     }
 }
 
-// per-segment minimum and maximum of a packed value array (the sector split of SectorizedFurthestSampling needs the
-// azimuth range of every cloud: pointops.py:70-71 takes .min()/.max() per cloud on the host)
-__device__ __forceinline__ void atomic_min_f(float *a, float v)
-{
-    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(v));
-    else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
-}
-__device__ __forceinline__ void atomic_max_f(float *a, float v)
-{
-    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(a), __float_as_int(v));
-    else atomicMin(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
-}
-__global__ void __launch_bounds__(TPB) segment_minmax_kernel(const float *__restrict__ v, const int *__restrict__ offset,
-                                                             float *__restrict__ vmin, float *__restrict__ vmax)
-{
-    const int seg = blockIdx.y;
-    const long beg = seg ? __ldg(offset + seg - 1) : 0, end = __ldg(offset + seg);
-    float lo = INFINITY, hi = -INFINITY;
-    for (long i = beg + blockIdx.x * (long)TPB + threadIdx.x; i < end; i += (long)gridDim.x * TPB) {
-        const float x = __ldg(v + i);
-        lo = fminf(lo, x);
-        hi = fmaxf(hi, x);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0 && lo <= hi) {
-        atomic_min_f(vmin + seg, lo);
-        atomic_max_f(vmax + seg, hi);
-    }
-}
-
 }  // namespace
 
 #define RSB_LAUNCH_1D(kern, work, ...)                                         \
@@ -361,15 +327,3 @@ RSB_EXPORT int rsb_group_rows_backward(long rows, int P4, int Cn, int Cf, int ld
     return 0;
 }
 
-RSB_EXPORT int rsb_segment_minmax(int b, long n_max, const float *values, const int *offset, float *vmin, float *vmax,
-                                  cudaStream_t stream)
-{
-    if (b == 0) return 0;
-    long slices = (n_max + TPB * 8 - 1) / (TPB * 8);
-    if (slices < 1) slices = 1;
-    if (slices > 64) slices = 64;
-    segment_minmax_kernel<<<dim3((unsigned)slices, (unsigned)b), TPB, 0, stream>>>(values, offset, vmin, vmax);
-    RSB_CHECK_LAUNCH("segment_minmax_kernel");
-    RSB_COUNT_LAUNCH(1);
-    return 0;
-}

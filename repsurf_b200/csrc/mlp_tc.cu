@@ -292,7 +292,14 @@ __device__ __forceinline__ void split4(const float *v, float4 &hi, float4 &lo)
 {
     hi.x = to_tf32(v[0]); hi.y = to_tf32(v[1]); hi.z = to_tf32(v[2]); hi.w = to_tf32(v[3]);
     // the residual goes to the tensor core unrounded (kind::tf32 truncates it; NaN survives): see tc_common.cuh split4
+#ifndef RSB_LO_RAW
+#define RSB_LO_RAW 1
+#endif
+#if RSB_LO_RAW
     lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
+#else
+    lo.x = to_tf32(v[0] - hi.x); lo.y = to_tf32(v[1] - hi.y); lo.z = to_tf32(v[2] - hi.z); lo.w = to_tf32(v[3] - hi.w);
+#endif
 }
 
 // column sums of a warp's 32x32 register tile through a padded shared tile; result for column `lane`

@@ -184,6 +184,7 @@ struct Rows2Params {
     const float *Wp;
     long rows;
     int N, NT, n_tiles, k_chunks, stages;
+    int nsub;         // an N tile is processed as nsub column slices of NT / nsub (when a full tile's weights do not fit a stage)
     int n_pieces;     // raw tensors behind the operand (1: RAW / BN_RELU, 2: DUAL / AFFINE2)
     int w_resident;   // the pre-split weights of all (N tile, K chunk) pairs stay in shared memory
     int v_bufs;       // staging tiles per epilogue warp for the outgoing block (1 or 2)
@@ -201,8 +202,10 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
     unsigned char *gbase = smem_raw + (base - raw0);
 
     const int NT = P.NT, S = P.stages, KCH = P.k_chunks;
-    const uint32_t w_chunk_bytes = 2u * (uint32_t)NT * KC * 4;
-    const uint32_t stage_bytes = 2 * A_TILE + (P.w_resident ? 0u : w_chunk_bytes);
+    const int NS = P.nsub, NTs = NT / NS;                            // column slice of an N tile
+    const uint32_t w_chunk_bytes = 2u * (uint32_t)NT * KC * 4;        // one (N tile, K chunk) of the pre-split weights: hi | lo
+    const uint32_t w_half = (uint32_t)NT * KC * 4, w_slice = (uint32_t)NTs * KC * 4;
+    const uint32_t stage_bytes = 2 * A_TILE + (P.w_resident ? 0u : 2u * w_slice);
     const uint32_t w_res = base + (uint32_t)S * stage_bytes;
     const uint32_t w_res_bytes = P.w_resident ? (uint32_t)(P.n_tiles * KCH) * w_chunk_bytes : 0u;
     const bool mask = P.E.kind == RSB_EPI_RELU_MASK;
@@ -247,7 +250,8 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
     const uint32_t tmem_base = cta_setup<512>(B, tid, warp, XF_THREADS + (P.w_resident ? 0 : 1));
 
     const long n_row_tiles = (P.rows + TM - 1) / TM;
-    const long n_work = n_row_tiles * P.n_tiles;
+    const int per_tile = P.n_tiles * NS;                               // work items of one row tile: (N tile, slice)
+    const long n_work = n_row_tiles * per_tile;
 
     if (warp < XF_WARPS) {
         // =============================== transform warps ===============================
@@ -301,8 +305,9 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
             }
             uint32_t it = 0;
             for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const long tile = w / P.n_tiles;
-                const int nt = (int)(w - tile * P.n_tiles);
+                const long tile = w / per_tile;
+                const int rem = (int)(w - tile * per_tile);
+                const int nt = rem / NS, sub = rem - nt * NS;
                 const int row0 = (int)(tile * TM);
                 for (int kc = 0; kc < KCH; kc++, it++) {
                     const int s = it % S;
@@ -312,19 +317,24 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
                     tma_load_2d(st, &P.mapA0, kc * KC, row0, &B->raw_full[s]);
                     if (P.n_pieces == 2) tma_load_2d(st + A_TILE, &P.mapA1, kc * KC, row0, &B->raw_full[s]);
                     if (!P.w_resident) {
-                        mbar_arrive_expect_tx(&B->full[s], w_chunk_bytes);
-                        bulk_g2s(st + 2 * A_TILE, P.Wp + ((size_t)nt * KCH + kc) * (2 * (size_t)NT * KC), w_chunk_bytes, &B->full[s]);
+                        // slice `sub` of the chunk: rows sub*NTs .. of the hi block, then of the lo block (8-row groups of the
+                        // canonical layout are 1024 B apart, so a slice is contiguous inside each block)
+                        const float *wc = P.Wp + ((size_t)nt * KCH + kc) * (2 * (size_t)NT * KC) + (size_t)sub * NTs * KC;
+                        mbar_arrive_expect_tx(&B->full[s], 2u * w_slice);
+                        bulk_g2s(st + 2 * A_TILE, wc, w_slice, &B->full[s]);
+                        bulk_g2s(st + 2 * A_TILE + w_slice, wc + (size_t)NT * KC, w_slice, &B->full[s]);
                     }
                 }
             }
         }
     } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================
-        const uint32_t idesc = umma_idesc_tf32(TM, NT, false);
+        const uint32_t idesc = umma_idesc_tf32(TM, NTs, false);
         if (P.w_resident) mbar_wait(&B->w_bar, 0);
         uint32_t it = 0, acc_it = 0;
         for (long w = blockIdx.x; w < n_work; w += gridDim.x, acc_it++) {
-            const int nt = (int)(w % P.n_tiles);
+            const int rem = (int)(w % per_tile);
+            const int nt = rem / NS, sub = rem - nt * NS;
             const int ab = acc_it & 1;
             mbar_wait(&B->acc_empty[ab], ((acc_it >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -336,8 +346,8 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
                 if (lane == 0) {
                     const uint32_t st = base + (uint32_t)s * stage_bytes;
                     const uint32_t a_hi = st, a_lo = st + A_TILE;
-                    const uint32_t b_hi = P.w_resident ? w_res + (uint32_t)(nt * KCH + kc) * w_chunk_bytes : st + 2 * A_TILE;
-                    const uint32_t b_lo = b_hi + (uint32_t)NT * KC * 4;
+                    const uint32_t b_hi = P.w_resident ? w_res + (uint32_t)(nt * KCH + kc) * w_chunk_bytes + (uint32_t)sub * w_slice : st + 2 * A_TILE;
+                    const uint32_t b_lo = b_hi + (P.w_resident ? w_half : w_slice);
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ks++) {
                         // A: K-major SWIZZLE_128B (8 tf32 = 32 B inside the 128-byte row); W: canonical no-swizzle K-major
@@ -366,19 +376,21 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
         const int sw = lane & 7;
         uint32_t acc_it = 0, vb = 0;
         for (long w = blockIdx.x; w < n_work; w += gridDim.x, acc_it++) {
-            const long tile = w / P.n_tiles;
-            const int nt = (int)(w - tile * P.n_tiles);
+            const long tile = w / per_tile;
+            const int rem = (int)(w - tile * per_tile);
+            const int nt = rem / NS, sub = rem - nt * NS;
+            const int col0 = nt * NT + sub * NTs;              // first output column of this work item
             const int ab = acc_it & 1;
             const long row = tile * TM + q * 32 + lane;
             const bool row_ok = row < P.rows;
             mbar_wait(&B->acc_full[ab], (acc_it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
-            const int ncols = min(NT, P.N - nt * NT);
+            const int ncols = min(NTs, P.N - col0);
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + c0, v);
-                const int nl = nt * NT + c0;                       // first column of the block (table index == column)
+                const int nl = col0 + c0;                          // first column of the block (table index == column)
                 // the staging tile of this block must have been read by its previous TMA store
                 if (P.has_y) {
                     if (lane == 0) { if (P.v_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
@@ -466,8 +478,8 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
                     }
                     const int n = nl + lane;
                     if (P.smem_stats) {
-                        if (c0 + lane < NT) {               // NT is a multiple of 16, not of 32
-                            double *a = my_acc + c0 + lane;
+                        if (c0 + lane < NTs) {              // a slice is a multiple of 16 columns, not of 32
+                            double *a = my_acc + sub * NTs + c0 + lane;
                             a[0] += (double)s0;
                             a[NT] += (double)s1;
                             if (n_stat == 3) a[2 * NT] += (double)s2;
@@ -761,26 +773,32 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
     const size_t w_total = (size_t)n_tiles * P.k_chunks * w_chunk;
     const int Npad = n_tiles * NT;
     bool fit = false;
-    for (int vb = 2; vb >= 1 && !fit; vb--) {
-        const int epi_tiles = vb + (mask ? (E->dual ? 2 : 1) : 0);
-        const size_t fixed = 4 * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 + (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0) +
-                             sizeof(Bars2) + 1024 + 64;
-        if (fixed + 2 * (2 * (size_t)A_TILE) > (size_t)SMEM_MAX) continue;
-        const size_t budget = SMEM_MAX - fixed;
-        for (int res = 1; res >= 0 && !fit; res--) {
-            if (res && w_total > 64 * 1024) continue;
-            const size_t stage_b = 2 * (size_t)A_TILE + (res ? 0 : w_chunk);
-            if (budget < (res ? w_total : 0) + 2 * stage_b) continue;
-            int st = (int)((budget - (res ? w_total : 0)) / stage_b);
-            if (st > STAGES_MAX) st = STAGES_MAX;
-            if (res && st < 3) continue;           // residency must not starve the pipeline
-            P.stages = st; P.w_resident = res; P.v_bufs = vb;
-            fit = true;
+    for (int ns = 1; ns <= 2 && !fit; ns++) {
+        // a full tile's weight chunk (up to 64 KB) may not leave room for two pipeline stages next to the epilogue's
+        // staging tiles: then the tile is processed as two column slices (the operand tile is staged once per slice)
+        if (ns == 2 && (NT % 32)) break;
+        const size_t w_stage = w_chunk / ns;
+        for (int vb = 2; vb >= 1 && !fit; vb--) {
+            const int epi_tiles = vb + (mask ? (E->dual ? 2 : 1) : 0);
+            const size_t fixed = 4 * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 + (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0) +
+                                 sizeof(Bars2) + 1024 + 64;
+            if (fixed + 2 * (2 * (size_t)A_TILE) > (size_t)SMEM_MAX) continue;
+            const size_t budget = SMEM_MAX - fixed;
+            for (int res = 1; res >= 0 && !fit; res--) {
+                if (res && (w_total > 64 * 1024 || ns > 1)) continue;
+                const size_t stage_b = 2 * (size_t)A_TILE + (res ? 0 : w_stage);
+                if (budget < (res ? w_total : 0) + 2 * stage_b) continue;
+                int st = (int)((budget - (res ? w_total : 0)) / stage_b);
+                if (st > STAGES_MAX) st = STAGES_MAX;
+                if (res && st < 3) continue;           // residency must not starve the pipeline
+                P.stages = st; P.w_resident = res; P.v_bufs = vb; P.nsub = ns;
+                fit = true;
+            }
         }
     }
     if (!fit) return -1;
     const int epi_tiles = P.v_bufs + (mask ? (E->dual ? 2 : 1) : 0);
-    const size_t stage_b = 2 * (size_t)A_TILE + (P.w_resident ? 0 : w_chunk);
+    const size_t stage_b = 2 * (size_t)A_TILE + (P.w_resident ? 0 : w_chunk / P.nsub);
     const size_t smem = (size_t)P.stages * stage_b + (P.w_resident ? w_total : 0) + 4 * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 +
                         (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0) + sizeof(Bars2) + 1024 + 64;
 
@@ -799,7 +817,7 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
         RSB_CUDA(cudaFuncSetAttribute(gemm_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         attr_set = true;
     }
-    const long n_work = ((rows + TM - 1) / TM) * n_tiles;
+    const long n_work = ((rows + TM - 1) / TM) * n_tiles * P.nsub;
     const int grid = (int)(n_work < rsb_sm_count() ? n_work : rsb_sm_count());
     gemm_rows2_kernel<<<grid, THREADS2, smem, stream>>>(P);
     RSB_CHECK_LAUNCH("gemm_rows2_kernel");

@@ -81,6 +81,13 @@ class RepSurfSeg(nn.Module):
 
     def forward(self, pos_feat_off0):
         coord, feat, offset = pos_feat_off0
+        # sampling / neighbour search of all four levels start now on side streams (they depend on coordinates only) and
+        # overlap the umbrella constructor and the shared MLPs; the modules below pick the results up
+        sas = (self.sa1, self.sa2, self.sa3, self.sa4)
+        with seg_m.GeometryPlan(coord, offset, [(m.stride, m.nsample, m.num_sector) for m in sas], self.training):
+            return self._forward(coord, feat, offset)
+
+    def _forward(self, coord, feat, offset):
         l0 = [coord, self.surface_constructor(coord, offset), torch.cat([coord, feat], 1), offset]
         l1 = self.sa1(l0)
         l2 = self.sa2(l1)

@@ -34,22 +34,123 @@ def strided_offsets(offset, stride):
     return P.make_offsets(out, offset.device)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Geometry plan: sampling and neighbour search of ALL levels depend on the coordinates only (never on features), so a
+# caller that knows the level structure can start them ahead, on side streams, while the main stream runs the umbrella
+# constructor and the shared MLPs: the FPS launches occupy a few SMs for milliseconds (one CTA cluster per segment) and
+# hide completely behind the GEMMs.  The modules pick the results up by the identity of their `center` tensor; without
+# an active plan they compute everything themselves, in order, on the current stream (same results either way).
+# ---------------------------------------------------------------------------------------------------------------
+_ACTIVE_PLAN = None
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _SIDE_STREAMS[key]
+
+
+def _sample(stride, center, offset, num_sector, training):
+    """FPS of one level -> (fps_idx int64, new_center, new_offset); ref: segmentation/modules/repsurface_utils.py:24-33."""
+    new_offset = strided_offsets(offset, stride)
+    if num_sector > 1 and training:
+        fps_idx = P.sectorized_fps(center, offset, new_offset, num_sector)
+    else:
+        fps_idx = P.furthestsampling(center, offset, new_offset).long()
+    return fps_idx, center[fps_idx, :], new_offset
+
+
+class GeometryPlan:
+    """levels: [(stride, nsample, num_sector)] of consecutive SurfaceAbstractionCD blocks starting at (center, offset);
+    fp_k: neighbours of the feature-propagation interpolation between consecutive levels (None = not prefetched)."""
+
+    def __init__(self, center, offset, levels, training, fp_k=3):
+        dev = center.device
+        main = torch.cuda.current_stream(dev)
+        s_fps, s_knn = _side_streams(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        self.sa, self.knn = {}, {}
+        chain = []
+        cur_c, cur_o = center, offset
+        with torch.cuda.stream(s_fps):
+            s_fps.wait_event(start)
+            for stride, nsample, num_sector in levels:
+                if stride > 1:
+                    fps_idx, new_c, new_o = _sample(stride, cur_c, cur_o, num_sector, training)
+                else:
+                    fps_idx, new_c, new_o = None, cur_c, cur_o
+                ev = torch.cuda.Event()
+                ev.record(s_fps)
+                chain.append(dict(center=cur_c, offset=cur_o, key=(stride, nsample, num_sector > 1 and training), fps_idx=fps_idx,
+                                  new_center=new_c, new_offset=new_o, ev_fps=ev))
+                cur_c, cur_o = new_c, new_o
+        with torch.cuda.stream(s_knn):
+            s_knn.wait_event(start)
+            for lv in chain:
+                s_knn.wait_event(lv["ev_fps"])
+                lv["group_idx"], _ = P.knnquery(lv["key"][1], lv["center"], lv["new_center"], lv["offset"], lv["new_offset"])
+                lv["ev"] = torch.cuda.Event()
+                lv["ev"].record(s_knn)
+            if fp_k is not None:
+                for lv in reversed(chain):                      # coarse <- fine, in the order the decoder asks for them
+                    if lv["fps_idx"] is None:
+                        continue
+                    idx, dist = P.knnquery(fp_k, lv["new_center"], lv["center"], lv["new_offset"], lv["offset"])
+                    ev = torch.cuda.Event()
+                    ev.record(s_knn)
+                    self.knn[(fp_k, id(lv["new_center"]), id(lv["center"]))] = (idx, dist, ev, lv["new_center"], lv["center"])
+        for lv in chain:
+            # side-stream allocations used by the main stream: tell the caching allocator
+            for t in (lv["fps_idx"], lv["new_center"], lv["group_idx"]):
+                if t is not None and t is not center:
+                    t.record_stream(main)
+            self.sa[id(lv["center"])] = lv
+        for idx, dist, _ev, _a, _b in self.knn.values():
+            idx.record_stream(main)
+            dist.record_stream(main)
+
+    def __enter__(self):
+        global _ACTIVE_PLAN
+        self._prev, _ACTIVE_PLAN = _ACTIVE_PLAN, self
+        return self
+
+    def __exit__(self, *exc):
+        global _ACTIVE_PLAN
+        _ACTIVE_PLAN = self._prev
+        return False
+
+    def level(self, center, stride, nsample, sectorized):
+        lv = self.sa.get(id(center))
+        if lv is None or lv["center"] is not center or lv["key"] != (stride, nsample, sectorized):
+            return None
+        torch.cuda.current_stream(center.device).wait_event(lv["ev"])
+        return lv
+
+    def neighbours(self, k, xyz, new_xyz):
+        ent = self.knn.get((k, id(xyz), id(new_xyz)))
+        if ent is None or ent[3] is not xyz or ent[4] is not new_xyz:
+            return None
+        torch.cuda.current_stream(xyz.device).wait_event(ent[2])
+        return ent[0], ent[1]
+
+
 def _sample_and_group(stride, nsample, center, normal, feature, offset, return_polar, num_sector, training):
     """ref: segmentation/modules/repsurface_utils.py:15-51.
-    -> new_center [M,3], new_normal [M,Cn], rows [M*ns, C4] ([rel xyz, polar? | pad | normal, feature? | pad], see
-       mlp.pack_rows), (first feature column, feature channels), new_offset."""
-    if stride > 1:
-        new_offset = strided_offsets(offset, stride)
-        if num_sector > 1 and training:
-            fps_idx = P.sectorized_fps(center, offset, new_offset, num_sector)
-        else:
-            fps_idx = P.furthestsampling(center, offset, new_offset)
-        fps_idx = fps_idx.long()
-        new_center = center[fps_idx, :]
-        new_normal = normal[fps_idx, :]
+    -> new_center [M,3], new_normal [M,Cn], rows [M*ns, C4] ([rel xyz, polar? | pad | normal, feature? | pad], csrc/group.cu
+       group_rows_fwd), (first feature column, feature channels), new_offset."""
+    lv = _ACTIVE_PLAN.level(center, stride, nsample, num_sector > 1 and training) if _ACTIVE_PLAN is not None else None
+    if lv is not None:
+        fps_idx, new_center, new_offset, group_idx = lv["fps_idx"], lv["new_center"], lv["new_offset"], lv["group_idx"]
     else:
-        new_center, new_normal, new_offset = center, normal, offset
-    group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
+        if stride > 1:
+            fps_idx, new_center, new_offset = _sample(stride, center, offset, num_sector, training)
+        else:
+            fps_idx, new_center, new_offset = None, center, offset
+        group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
+    new_normal = normal[fps_idx, :] if fps_idx is not None else normal
     rows, layout = group_rows(center, new_center, group_idx, normal, feature, nsample, return_polar)
     return new_center, new_normal, rows, layout, new_offset
 
@@ -108,7 +209,8 @@ class SurfaceFeaturePropagationCD(nn.Module):
     def forward(self, pos_feat_off1, pos_feat_off2):
         xyz1, points1, offset1 = pos_feat_off1
         xyz2, points2, offset2 = pos_feat_off2
-        idx, dist = P.knnquery(3, xyz2, xyz1, offset2, offset1)             # coarse neighbours of every fine point
+        pre = _ACTIVE_PLAN.neighbours(3, xyz2, xyz1) if _ACTIVE_PLAN is not None else None
+        idx, dist = pre if pre is not None else P.knnquery(3, xyz2, xyz1, offset2, offset1)   # coarse neighbours of every fine point
         weight = P._idw(dist).contiguous()
         coarse = tc.linear_bn(points2, self.mlp_f0, self.norm_f0, relu=False)   # projected BEFORE interpolation (:267)
         x = P._InterpApply.apply(coarse, idx, weight)

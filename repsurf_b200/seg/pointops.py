@@ -61,6 +61,8 @@ def const_tensor(values, dtype, device):
         t = torch.tensor(list(values), dtype=dtype)
         if torch.device(device).type == "cuda":
             t = t.pin_memory().to(device, non_blocking=True)
+            # the constant is shared by every later call on ANY stream: finish the upload once, here (first use only)
+            torch.cuda.current_stream(t.device).synchronize()
         _CONST[key] = t
     return t
 
@@ -100,25 +102,14 @@ class FurthestSampling(Function):
 furthestsampling = FurthestSampling.apply
 
 
-def _linspace_f32(start, end, steps):
-    """torch.linspace(start, end, steps) in fp32, element by element as ATen's CPU kernel computes it
-    (aten/src/ATen/native/RangeFactories.cpp: step=(end-start)/(steps-1); i < steps/2 ? start+step*i :
-    end-step*(steps-1-i)), vectorised over clouds: start/end are [B] tensors -> [B, steps]."""
-    step = (end - start) / float(steps - 1)
-    i = torch.arange(steps, device=start.device, dtype=torch.float32)
-    lo = start[:, None] + step[:, None] * i[None, :]
-    hi = end[:, None] - step[:, None] * (float(steps - 1) - i)[None, :]
-    return torch.where((i < steps // 2)[None, :], lo, hi)
-
-
 class SectorizedFurthestSampling(Function):
     """ref: pointops.py:52-111.  Azimuth-sectorized FPS; returns int64 global row ids, sector-major per cloud.
 
-    The reference does the sector split in host Python (per cloud and per sector `torch.where`,
-    `.item()`); here it is a handful of device ops (segment min/max, bucket, stable sort) followed by
-    ONE packed FPS launch over all (cloud, sector) segments, with no host synchronisation: the sector
-    sizes stay on the device and the kernel derives the reference's tie rule from the device-side
-    maximum (rsb_furthestsampling_packed n_max_dev)."""
+    The reference does the sector split in host Python (per cloud and per sector `torch.where`, `.item()`); here it is
+    csrc/sector.cu (angles + per-cloud range, classification against the fp32 linspace edges, stable counting sort)
+    followed by ONE packed FPS launch over all (cloud, sector) segments and a map-back kernel, with no host
+    synchronisation: the sector sizes stay on the device and the FPS kernel derives the reference's tie rule from the
+    device-side maximum (rsb_furthestsampling_packed_bounded)."""
 
     @staticmethod
     def forward(ctx, xyz, offset, new_offset, num_sectors, min_points=10000):
@@ -141,22 +132,14 @@ class SectorizedFurthestSampling(Function):
             run += q
             acc_q.append(run)
         new_sector_offset = const_tensor(acc_q, torch.int32, dev)
-
-        cloud = torch.repeat_interleave(torch.arange(b, device=dev), const_tensor(sizes, torch.int64, dev), output_size=n)
-        angle = torch.atan2(xyz[:, 0], xyz[:, 1])
-        amin = torch.full((b,), float("inf"), device=dev)
-        amax = torch.full((b,), float("-inf"), device=dev)
-        N.call("rsb_segment_minmax", b, max(sizes), angle, offset, amin, amax)
-        edges = _linspace_f32(amin, amax + 1e-4, num_sectors + 1)              # [b, S+1]
-        # sector s  <=>  edges[s] <= angle < edges[s+1]   (count of inner edges <= angle)
-        sec = (angle[:, None] >= edges[cloud][:, 1:num_sectors]).sum(1)
-        nsec_t = const_tensor(nsec, torch.int64, dev)
-        sec = torch.where(nsec_t[cloud] > 1, sec, torch.zeros_like(sec))
-        seg_id = const_tensor(seg_first, torch.int64, dev)[cloud] + sec
-        order = torch.sort(seg_id, stable=True)[1]                             # sector-major, ascending index inside
-        counts = torch.bincount(seg_id, minlength=nseg)
-        sector_offset = counts.cumsum(0).to(torch.int32)
-        sector_xyz = xyz[order].contiguous()
+        nbytes = int(N.lib().rsb_sector_split_workspace_bytes(n, b, nseg))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        order = torch.empty(n, dtype=torch.int32, device=dev)
+        sector_xyz = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        sector_offset = torch.empty(nseg, dtype=torch.int32, device=dev)
+        count_max = torch.empty(1, dtype=torch.int32, device=dev)
+        N.call("rsb_sector_split", b, n, int(num_sectors), nseg, xyz, offset, const_tensor(nsec, torch.int32, dev),
+               const_tensor(seg_first, torch.int32, dev), ws, nbytes, order, sector_xyz, sector_offset, count_max)
         idx = torch.empty(noff[-1], dtype=torch.int32, device=dev)
         # The sector sizes exist on the device only.  No read-back: sectors of up to 1.1x the mean size take a launch
         # planned for that size, anything larger a second launch planned for the whole cloud (it exits at once when the
@@ -165,11 +148,12 @@ class SectorizedFurthestSampling(Function):
         # points (pigeonhole), else taken from the device-side maximum.
         mean_sector = max(-(-sz // k) for sz, k in zip(sizes, nsec))
         n_expect = min(max(sizes), mean_sector + mean_sector // 10 + 1)
-        n_max_dev = None if mean_sector >= 1024 else counts.max().to(torch.int32).reshape(1)
+        n_max_dev = None if mean_sector >= 1024 else count_max
         tmp = torch.empty(n, device=dev) if max(sizes) + 1024 > _FPS_REGISTER_CAPACITY else None
         N.call("rsb_furthestsampling_packed_bounded", nseg, n_expect, max(sizes), n_max_dev, sector_xyz, sector_offset,
                new_sector_offset, tmp, idx, None)
-        out = order[idx.long()]
+        out = torch.empty(noff[-1], dtype=torch.int64, device=dev)
+        N.call("rsb_sector_map_back", noff[-1], order, idx, out)
         ctx.mark_non_differentiable(out)
         return out
 

@@ -146,7 +146,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(0)
     small = [(1000, 32, 32, "raw", "stats"), (1000, 20, 64, "raw", "stats"), (777, 64, 32, "dual", "stats"), (5000, 96, 128, "bn", "stats"),
              (3000, 64, 64, "aff", "mask"), (3000, 32, 64, "aff", "maskdual"), (2000, 272, 512, "bn", "stats"), (129, 40, 48, "bn", "none"),
-             (300, 256, 272, "aff", "none")]
+             (300, 256, 272, "aff", "none"), (3000, 512, 256, "raw", "mask"), (3000, 256, 256, "aff", "mask"), (1000, 1024, 512, "raw", "mask")]
     for c in small:
         run_rows(*c, g)
     smallw = [(1000, 64, 20, "aff", "raw"), (1000, 32, 64, "aff", "dual"), (2077, 64, 32, "raw", "bn"), (4000, 128, 128, "affwrap", "raw"),
@@ -160,7 +160,7 @@ def main():
            (R1, 64, 32, "raw", "mask"), (R1, 32, 32, "aff", "maskdual"), (R1, 32, 16, "aff", "none"),
            (R2, 80, 128, "raw", "stats"), (R2, 64, 64, "dual", "stats"), (R2, 64, 128, "bn", "stats"), (R2, 128, 64, "raw", "mask"),
            (R3, 144, 256, "raw", "stats"), (R3, 128, 256, "bn", "stats"), (R4, 272, 512, "raw", "stats"), (R4, 256, 512, "bn", "stats"),
-           (327680, 128, 128, "raw", "stats"), (327680, 128, 128, "aff", "none")]
+           (327680, 128, 128, "raw", "stats"), (327680, 128, 128, "aff", "none"), (R4, 512, 256, "raw", "mask"), (R4, 256, 256, "aff", "mask")]
     for c in big:
         run_rows(*c, g)
     bigw = [(R1, 64, 20, "affwrap", "raw"), (R1, 32, 32, "aff", "dual"), (R1, 64, 32, "raw", "bn"),

@@ -80,11 +80,12 @@ def _rel(a, b):
 def test_fused_sa_mlp_matches_fp64_torch(G, ns, pos_c, feat_c, mlp, conv, train):
     """Fused shared MLP + max-pool (tc.sa_mlp_fused) against the same nn modules evaluated in fp64, in training mode
     (batch statistics, running-buffer side effects) and in eval mode (running statistics; backward = frozen BatchNorm).
-    The max-pool routing of the checker is pinned to the kernel's arg-max (it is only piecewise differentiable: an
-    fp32-vs-fp64 tie flip moves a whole gradient row), so gradients are compared at 1e-4."""
+    The routing of the checker (max-pool arg-max, ReLU masks) is pinned to the kernel's own decisions: both are only
+    piecewise differentiable and an fp32-vs-fp64 flip of one near-zero element moves a whole gradient row.  The free
+    fp64 evaluation is compared on the forward values; gradients, with the routing fixed, at 1e-4."""
     import copy
     from repsurf_b200 import tc
-    from tests.torch_ref import sa_mlp_rows
+    from tests.torch_ref import kernel_relu_masks, sa_mlp_rows
     torch.manual_seed(G + ns)
     blk = _Block(pos_c, feat_c, mlp, conv).to(cuda)
     with torch.no_grad():
@@ -101,7 +102,7 @@ def test_fused_sa_mlp_matches_fp64_torch(G, ns, pos_c, feat_c, mlp, conv, train)
     arg = out.grad_fn.saved[-1]                          # [G, C'] sample index the kernel pooled
     free = sa_mlp_rows(Xb.detach(), pos_c, copy.deepcopy(ref), ns)
     assert _rel(out, free) < 1e-5                        # the free max-pool agrees on the values
-    want = sa_mlp_rows(Xb, pos_c, ref, ns, arg=arg)
+    want = sa_mlp_rows(Xb, pos_c, ref, ns, arg=arg, masks=kernel_relu_masks(out.grad_fn))
     assert _rel(out, want) < 1e-5
     go = torch.randn_like(out)
     out.backward(go)
@@ -156,8 +157,13 @@ def test_linear_bn_layer_matches_fp64_torch(R, K, Nn, relu, train):
     xa, xb = xp.clone().requires_grad_(True), x.double().requires_grad_(True)
     out = tc.linear_bn(xa, lin, bn, relu)
     want = bn2(lin2(xb))
-    want = torch.relu(want) if relu else want
-    assert out.shape[1] == (Nn + 3) // 4 * 4 and float(out[:, Nn:].abs().sum()) == 0.0
+    if relu:
+        # ReLU decisions pinned to the kernel's (z = fma(Y, sc, sh) in fp32 from its stored pre-BatchNorm output)
+        _X, _W, Ysv, sc, sh = out.grad_fn.saved[:5]
+        mask = ((Ysv.double() * sc.double() + sh.double()).float() > 0)[:, :Nn]
+        assert _rel(out[:, :Nn].detach(), torch.relu(want).detach()) < 1e-5
+        want = want * mask.double()
+    assert out.shape[1] == (Nn + 3) // 4 * 4 and float(out[:, Nn:].detach().abs().sum()) == 0.0
     assert _rel(out[:, :Nn], want) < 1e-5
     go = torch.randn_like(want).float()
     gop = torch.zeros_like(out)
