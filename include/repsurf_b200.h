@@ -121,6 +121,22 @@ int rsb_sector_split(int b, int n, int num_sectors, int nseg, const float *xyz, 
                      int *sector_offset, int *count_max, cudaStream_t stream);
 int rsb_sector_map_back(int m, const int *order, const int *idx, long long *out, cudaStream_t stream);
 
+/* replaces subtraction_forward/backward_cuda_launcher(n,nsample,c,...)     seg/po/src/subtraction/subtraction_cuda_kernel.h:11-12
+ * output[n,s,c] = input1[n,c] - input2[idx[n,s],c] (bit-exact).  Backward: grad_input1 is WRITTEN (fixed-order sum over the
+ * samples), grad_input2 accumulated by atomics (zero it first), as the reference's Python does (pointops.py:211-214). */
+int rsb_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2, const int *idx,
+                            float *output, cudaStream_t stream);
+int rsb_subtraction_backward(int n, int nsample, int c, const int *idx, const float *grad_output, float *grad_input1,
+                             float *grad_input2, cudaStream_t stream);
+/* replaces aggregation_forward/backward_cuda_launcher(n,nsample,c,w_c,...) seg/po/src/aggregation/aggregation_cuda_kernel.h:11-12
+ * output[n,c] = sum_s (input[idx[n,s],c] + position[n,s,c]) * weight[n,s,c % w_c] (bit-exact: ascending s, one fma per
+ * sample).  Backward: grad_position / grad_weight written, grad_input accumulated by atomics (zero it first). */
+int rsb_aggregation_forward(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                            const float *weight, const int *idx, float *output, cudaStream_t stream);
+int rsb_aggregation_backward(int n, int nsample, int c, int w_c, const float *input, const float *position,
+                             const float *weight, const int *idx, const float *grad_output, float *grad_input,
+                             float *grad_position, float *grad_weight, cudaStream_t stream);
+
 /* replaces knnquery_cuda_launcher(m,nsample,xyz,new_xyz,offset,new_offset,idx,dist2)   seg/po/src/knnquery/knnquery_cuda_kernel.h:11
  * adds b (= number of clouds).  dist [m,nsample]: squared distances, or their square roots when sqrt_out != 0
  * (fuses the torch.sqrt of seg/po/functions/pointops.py:127).  1 <= nsample <= 100. */
@@ -288,6 +304,15 @@ int rsb_bn_relu_backward(long rows, int C, float *dA, int ldd, const float *Y, i
 int rsb_bn_backward_coef(int C, long rows, const double *stats, int dual, const float *sc, const float *mu,
                          const float *inv, float *a, float *b, float *d, float *dgamma, float *dbeta,
                          cudaStream_t stream);
+
+/* ------------------------------------------------------------------ whole-scene inference (segmentation/tool/test_s3dis.py)
+ * rsb_scene_vote:   pred[idx[r], :] += softmax(logits[r, :]), count[idx[r]] += 1     test_s3dis.py:208-213 (logits row pitch ld)
+ * rsb_scene_decide: label[p] = argmax_c pred[p, c] / count[p]                        test_s3dis.py:217
+ * rsb_label_median: out[p] = lower median of label[nbr[p, 0..k)], k <= 128           util/utils.py:242-244 (torch.median) */
+int rsb_scene_vote(long rows, int num_class, const float *logits, int ld, const long long *idx, float *pred, float *count,
+                   cudaStream_t stream);
+int rsb_scene_decide(long n, int num_class, const float *pred, const float *count, int *label, cudaStream_t stream);
+int rsb_label_median(long n, int k, const int *nbr, const int *label, int *out, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O2 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared -std=c++17 -ccbin /usr/bin/g++ $TORCH_INC $PY_INC -D_GLIBCXX_USE_CXX11_ABI=1 -w"
 build() {  # tree name
   local src="$REF/$1/modules/pointops/src"
-  local files=$(ls "$src"/*/*_cuda_kernel.cu | grep -v -E "subtraction|aggregation")
+  local files=$(ls "$src"/*/*_cuda_kernel.cu)
   $NVCC $FLAGS -o "$OUT/libref_pointops_$2.so" $files
   echo "built $OUT/libref_pointops_$2.so"
 }

@@ -250,6 +250,37 @@ def interp_packed_bwd(grad_out, idx, weight, m):
     return g
 
 
+def subtraction_fwd(in1, in2, idx):
+    n, c = in1.shape
+    ns = idx.shape[1]
+    out = torch.empty(n, ns, c, dtype=torch.float32)
+    lib().orc_subtraction_fwd(_c_int(n), _c_int(ns), _c_int(c), _p(in1), _p(in2), _p(idx), _p(out))
+    return out
+
+
+def subtraction_bwd(grad_out, idx):
+    n, ns, c = grad_out.shape
+    g1, g2 = torch.zeros(n, c, dtype=torch.float32), torch.zeros(n, c, dtype=torch.float32)
+    lib().orc_subtraction_bwd(_c_int(n), _c_int(ns), _c_int(c), _p(idx), _p(grad_out), _p(g1), _p(g2))
+    return g1, g2
+
+
+def aggregation_fwd(inp, pos, w, idx):
+    n, ns, c = pos.shape
+    out = torch.zeros(n, c, dtype=torch.float32)
+    lib().orc_aggregation_fwd(_c_int(n), _c_int(ns), _c_int(c), _c_int(w.shape[-1]), _p(inp), _p(pos), _p(w), _p(idx), _p(out))
+    return out
+
+
+def aggregation_bwd(inp, pos, w, idx, grad_out):
+    n, ns, c = pos.shape
+    w_c = w.shape[-1]
+    g_in, g_pos, g_w = torch.zeros(n, c), torch.zeros(n, ns, c), torch.zeros(n, ns, w_c)
+    lib().orc_aggregation_bwd(_c_int(n), _c_int(ns), _c_int(c), _c_int(w_c), _p(inp), _p(pos), _p(w), _p(idx), _p(grad_out),
+                              _p(g_in), _p(g_pos), _p(g_w))
+    return g_in, g_pos, g_w
+
+
 # ----------------------------------------------------------------------------------------------
 # stand-in for the reference's pybind module (golden-vector generation only)
 # ----------------------------------------------------------------------------------------------

@@ -442,3 +442,58 @@ ORC_API void orc_interp_packed_bwd(int n, int c, int k, const float *grad_output
             for (int ch = 0; ch < c; ch++)
                 grad_input[(size_t)idx[p * k + i] * c + ch] += grad_output[p * c + ch] * weight[p * k + i];
 }
+
+/* ---- subtraction / aggregation (PointTransformer operators of the shared pointops package) -------------------------------
+ * follows segmentation/modules/pointops/src/subtraction/subtraction_cuda_kernel.cu:5-31 and
+ * segmentation/modules/pointops/src/aggregation/aggregation_cuda_kernel.cu:5-42.  The reference's backward kernels scatter
+ * with atomicAdd (order-dependent, rule R6): here the terms are added in ascending flat-thread-index order. */
+ORC_API void orc_subtraction_fwd(int n, int ns, int c, const float *in1, const float *in2, const int *idx, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (long row = 0; row < (long)n * ns; row++) {
+        const long p = row / ns, src = idx[row];
+        for (int ch = 0; ch < c; ch++) out[row * c + ch] = in1[p * c + ch] - in2[src * c + ch];
+    }
+}
+
+ORC_API void orc_subtraction_bwd(int n, int ns, int c, const int *idx, const float *go, float *g1, float *g2)
+{
+    for (long row = 0; row < (long)n * ns; row++) {
+        const long p = row / ns, src = idx[row];
+        for (int ch = 0; ch < c; ch++) {
+            g1[p * c + ch] += go[row * c + ch];
+            g2[src * c + ch] += -go[row * c + ch];
+        }
+    }
+}
+
+ORC_API void orc_aggregation_fwd(int n, int ns, int c, int w_c, const float *in, const float *pos, const float *w, const int *idx, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n * c; i++) {
+        const long p = i / c;
+        const int ch = (int)(i % c), wc = ch % w_c;
+        float acc = out[i];
+        for (int s = 0; s < ns; s++) {
+            const long src = idx[p * ns + s];
+            /* nvcc contracts `output += (a + b) * w` into one fma (SASS: FADD, FFMA) */
+            acc = fmaf(in[src * c + ch] + pos[(p * ns + s) * c + ch], w[(p * ns + s) * w_c + wc], acc);
+        }
+        out[i] = acc;
+    }
+}
+
+ORC_API void orc_aggregation_bwd(int n, int ns, int c, int w_c, const float *in, const float *pos, const float *w, const int *idx,
+                         const float *go, float *g_in, float *g_pos, float *g_w)
+{
+    for (long i = 0; i < (long)n * c; i++) {
+        const long p = i / c;
+        const int ch = (int)(i % c), wc = ch % w_c;
+        for (int s = 0; s < ns; s++) {
+            const long row = p * ns + s, src = idx[row];
+            g_in[src * c + ch] += go[i] * w[row * w_c + wc];
+            g_pos[row * c + ch] = go[i] * w[row * w_c + wc];
+            g_w[row * w_c + wc] += go[i] * (in[src * c + ch] + pos[row * c + ch]);
+        }
+    }
+}

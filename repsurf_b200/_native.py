@@ -34,6 +34,13 @@ _SIGS = {
     "rsb_interpolation_backward": [_i, _i, _i, _i, _p, _p, _p, _p],
     "rsb_furthestsampling_packed": [_i, _i, _p, _p, _p, _p, _p, _p, _p],
     "rsb_furthestsampling_packed_bounded": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "rsb_subtraction_forward": [_i, _i, _i, _p, _p, _p, _p],
+    "rsb_subtraction_backward": [_i, _i, _i, _p, _p, _p, _p],
+    "rsb_aggregation_forward": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "rsb_aggregation_backward": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rsb_scene_vote": [_l, _i, _p, _i, _p, _p, _p],
+    "rsb_scene_decide": [_l, _i, _p, _p, _p],
+    "rsb_label_median": [_l, _i, _p, _p, _p],
     "rsb_sector_split": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p],
     "rsb_sector_map_back": [_i, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],

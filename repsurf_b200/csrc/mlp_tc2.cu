@@ -41,6 +41,16 @@ constexpr int LOAD_WARP = XF_WARPS;     // TMA issuer
 constexpr int MMA_WARP = XF_WARPS + 1;  // tcgen05.mma issuer (also owns the TMEM allocation)
 constexpr int EPI_WARP0 = XF_WARPS + 2; // 4 epilogue warps
 constexpr int THREADS2 = (XF_WARPS + 2 + 4) * 32;
+// gemm_rows2 warp layouts.  The epilogue of a tile is a latency chain (tcgen05.ld -> [mask operand loads] -> staging -> TMA store
+// -> statistics read-back) of 2.5-6 us, longer than a tile's share of the HBM stream when K is small (ncu, profiles/r02_ncu_gemm.md:
+// issue slots 17-35 % busy, long-scoreboard stalls 9-25 per issue): there TWO epilogue warp sets alternate over the two TMEM
+// accumulator buffers and 8 warps suffice for the in-place operand transform.  With many K chunks per tile the transform is the
+// busier side: 16 transform warps, one epilogue set.  <XFW transform warps, ES epilogue sets of 4 warps>
+template <int XFW, int ES>
+struct RowsCfg {
+    static constexpr int XF_W = XFW, XF_T = XFW * 32, LOAD_W = XFW, MMA_W = XFW + 1, EPI_W0 = XFW + 2, EPI_N = 4 * ES,
+                         THREADS = (XFW + 2 + 4 * ES) * 32, PIECES = (TM * KC * 4 / 16) / (XFW * 32);
+};
 constexpr int STAGES_MAX = 4;
 constexpr int SMEM_MAX = 227 * 1024;
 
@@ -145,7 +155,7 @@ struct alignas(16) Bars2 {
 };
 
 template <int COLS>
-__device__ __forceinline__ uint32_t cta_setup(Bars2 *B, int tid, int warp, int full_count)
+__device__ __forceinline__ uint32_t cta_setup(Bars2 *B, int tid, int warp, int full_count, int mma_warp = MMA_WARP)
 {
     if (tid == 0) {
         for (int s = 0; s < STAGES_MAX; s++) { mbar_init(&B->raw_full[s], 1); mbar_init(&B->full[s], full_count); mbar_init(&B->empty[s], 1); }
@@ -153,7 +163,7 @@ __device__ __forceinline__ uint32_t cta_setup(Bars2 *B, int tid, int warp, int f
         mbar_init(&B->w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) {
+    if (warp == mma_warp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rsb_smem_addr(&B->tmem_slot)), "n"(COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -164,11 +174,11 @@ __device__ __forceinline__ uint32_t cta_setup(Bars2 *B, int tid, int warp, int f
 }
 
 template <int COLS>
-__device__ __forceinline__ void cta_teardown(uint32_t tmem_base, int warp)
+__device__ __forceinline__ void cta_teardown(uint32_t tmem_base, int warp, int mma_warp = MMA_WARP)
 {
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) {
+    if (warp == mma_warp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(COLS));
     }
@@ -193,8 +203,12 @@ struct Rows2Params {
     int has_y;
 };
 
-__global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_constant__ Rows2Params P)
+template <int XFW, int ES>
+__global__ void __launch_bounds__(RowsCfg<XFW, ES>::THREADS, 1) gemm_rows2_kernel(const __grid_constant__ Rows2Params P)
 {
+    typedef RowsCfg<XFW, ES> C;
+    constexpr int R_XF_WARPS = C::XF_W, R_XF_THREADS = C::XF_T, R_LOAD_WARP = C::LOAD_W, R_MMA_WARP = C::MMA_W, R_EPI_WARP0 = C::EPI_W0,
+                  R_EPI_WARPS = C::EPI_N, R_THREADS = C::THREADS, R_XF_PIECES = C::PIECES;
     extern __shared__ unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw0 = rsb_smem_addr(smem_raw);
@@ -213,16 +227,16 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
     const int epi_tiles = P.v_bufs + (mask ? (P.E.dual ? 2 : 1) : 0);
     const uint32_t epi0 = w_res + w_res_bytes;
     const int Npad = P.n_tiles * NT;
-    float *tabs = reinterpret_cast<float *>(gbase + (epi0 - base) + 4u * epi_tiles * 4096u);
+    float *tabs = reinterpret_cast<float *>(gbase + (epi0 - base) + (uint32_t)R_EPI_WARPS * epi_tiles * 4096u);
     double *sacc = reinterpret_cast<double *>(tabs + (size_t)P.n_tab * Npad);
-    Bars2 *B = reinterpret_cast<Bars2 *>(reinterpret_cast<unsigned char *>(sacc) + (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0));
+    Bars2 *B = reinterpret_cast<Bars2 *>(reinterpret_cast<unsigned char *>(sacc) + (P.smem_stats ? (size_t)R_EPI_WARPS * n_stat * NT * 8 : 0));
 
     const Opnd &A = P.A;
     const Epi &E = P.E;
 
     // ---- one-time shared-memory state ----
     // epilogue tables, zero-padded to the tile grid
-    for (int i = tid; i < P.n_tab * Npad; i += THREADS2) {
+    for (int i = tid; i < P.n_tab * Npad; i += R_THREADS) {
         const int t = i / Npad, n = i - t * Npad;
         float v = 0.f;
         if (n < P.N) {
@@ -236,27 +250,27 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
         tabs[i] = v;
     }
     if (P.smem_stats)
-        for (int i = tid; i < 4 * n_stat * NT; i += THREADS2) sacc[i] = 0.0;
+        for (int i = tid; i < R_EPI_WARPS * n_stat * NT; i += R_THREADS) sacc[i] = 0.0;
     // single-tensor operands: the "lo" tile is written by the transform only where channels exist; clear it once
     if (P.n_pieces == 1)
         for (int s = 0; s < S; s++)
-            for (int i = tid; i < A_TILE / 16; i += THREADS2) sts128(base + (uint32_t)s * stage_bytes + A_TILE + (uint32_t)i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int i = tid; i < A_TILE / 16; i += R_THREADS) sts128(base + (uint32_t)s * stage_bytes + A_TILE + (uint32_t)i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
     fence_proxy_async();
-    if (warp == LOAD_WARP && lane == 0) {
+    if (warp == R_LOAD_WARP && lane == 0) {
         prefetch_tmap(&P.mapA0);
         if (P.n_pieces == 2) prefetch_tmap(&P.mapA1);
         if (P.has_y) prefetch_tmap(&P.mapY);
     }
-    const uint32_t tmem_base = cta_setup<512>(B, tid, warp, XF_THREADS + (P.w_resident ? 0 : 1));
+    const uint32_t tmem_base = cta_setup<512>(B, tid, warp, R_XF_THREADS + (P.w_resident ? 0 : 1), R_MMA_WARP);
 
     const long n_row_tiles = (P.rows + TM - 1) / TM;
     const int per_tile = P.n_tiles * NS;                               // work items of one row tile: (N tile, slice)
     const long n_work = n_row_tiles * per_tile;
 
-    if (warp < XF_WARPS) {
+    if (warp < R_XF_WARPS) {
         // =============================== transform warps ===============================
-        // thread -> the 16-byte pieces tid and tid + 512 of the 128 x 32 tile (rows tid/8 and tid/8 + 64): both share
-        // (row & 7) and the physical chunk, hence the logical channel quad and its coefficients
+        // thread -> the 16-byte pieces tid + R_XF_THREADS j of the 128 x 32 tile (rows tid/8 + R_XF_THREADS/8 j): all share (row & 7)
+        // and the physical chunk, hence the logical channel quad and its coefficients
         const int q = (tid & 7) ^ ((tid >> 3) & 7);
         Coef cf;
         const bool hoist = KCH == 1;
@@ -275,28 +289,28 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
                 mbar_wait(&B->raw_full[s], (it / S) & 1);
                 const uint32_t a0 = base + (uint32_t)s * stage_bytes + (uint32_t)tid * 16;
                 if (nv > 0) {
-                    float4 u[2], x[2];
+                    float4 u[R_XF_PIECES], x[R_XF_PIECES];
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        u[j] = lds128(a0 + j * (XF_THREADS * 16));
-                        x[j] = two ? lds128(a0 + A_TILE + j * (XF_THREADS * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < R_XF_PIECES; j++) {
+                        u[j] = lds128(a0 + j * (R_XF_THREADS * 16));
+                        x[j] = two ? lds128(a0 + A_TILE + j * (R_XF_THREADS * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
+                    for (int j = 0; j < R_XF_PIECES; j++) {
                         float4 hi, lo;
                         split4(xform(A.kind, u[j], x[j], cf), hi, lo);
-                        sts128(a0 + j * (XF_THREADS * 16), hi);
-                        sts128(a0 + A_TILE + j * (XF_THREADS * 16), lo);
+                        sts128(a0 + j * (R_XF_THREADS * 16), hi);
+                        sts128(a0 + A_TILE + j * (R_XF_THREADS * 16), lo);
                     }
                 } else if (zero_lo) {
-                    sts128(a0 + A_TILE, make_float4(0.f, 0.f, 0.f, 0.f));
-                    sts128(a0 + A_TILE + XF_THREADS * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+                    for (int j = 0; j < R_XF_PIECES; j++) sts128(a0 + A_TILE + j * (R_XF_THREADS * 16), make_float4(0.f, 0.f, 0.f, 0.f));
                 }
                 fence_proxy_async();
                 mbar_arrive(&B->full[s]);
             }
         }
-    } else if (warp == LOAD_WARP) {
+    } else if (warp == R_LOAD_WARP) {
         // =============================== TMA issuer ===============================
         if (lane == 0) {
             if (P.w_resident) {
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == R_MMA_WARP) {
         // =============================== MMA issuer ===============================
         const uint32_t idesc = umma_idesc_tf32(TM, NTs, false);
         if (P.w_resident) mbar_wait(&B->w_bar, 0);
@@ -367,7 +381,8 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
     } else {
         // =============================== epilogue ===============================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int ew = warp - EPI_WARP0;        // staging / accumulator slot
+        const int ew = warp - R_EPI_WARP0;      // staging / statistics slot
+        const int eset = ew >> 2;               // set 0 drains accumulator buffer 0 (even work items), set 1 buffer 1
         const uint32_t my_epi = epi0 + (uint32_t)ew * epi_tiles * 4096u;
         const uint32_t p_tile = my_epi + (uint32_t)P.v_bufs * 4096u;   // mask epilogue: v*(yl-mu) tile(s)
         double *my_acc = sacc + (size_t)ew * n_stat * NT;
@@ -376,11 +391,12 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
         const int sw = lane & 7;
         uint32_t acc_it = 0, vb = 0;
         for (long w = blockIdx.x; w < n_work; w += gridDim.x, acc_it++) {
+            const int ab = acc_it & 1;
+            if (ES == 2 && ab != eset) continue;
             const long tile = w / per_tile;
             const int rem = (int)(w - tile * per_tile);
             const int nt = rem / NS, sub = rem - nt * NS;
             const int col0 = nt * NT + sub * NTs;              // first output column of this work item
-            const int ab = acc_it & 1;
             const long row = tile * TM + q * 32 + lane;
             const bool row_ok = row < P.rows;
             mbar_wait(&B->acc_full[ab], (acc_it >> 1) & 1);
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_rows2_kernel(const __grid_co
         }
         if (lane == 0) bulk_wait_all();
     }
-    cta_teardown<512>(tmem_base, warp);
+    cta_teardown<512>(tmem_base, warp, R_MMA_WARP);
 }
 
 // ============================================================================================================
@@ -772,35 +788,42 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
     const size_t w_chunk = 2 * (size_t)NT * KC * 4;
     const size_t w_total = (size_t)n_tiles * P.k_chunks * w_chunk;
     const int Npad = n_tiles * NT;
+    // warp layout: two epilogue sets when a tile has little transform work (K chunks x raw tensors) per epilogue pass
+    const int cfg2 = (P.k_chunks * P.n_pieces <= 4) ? 1 : 0;
+    const int R_EPI_WARPS = cfg2 ? 8 : 4;
     bool fit = false;
+    const int want_ss = P.smem_stats;
+    // preference order: whole N tiles before column slices, shared-memory statistics before per-tile atomics, two staging
+    // tiles per epilogue warp before one, resident weights before streamed ones
     for (int ns = 1; ns <= 2 && !fit; ns++) {
         // a full tile's weight chunk (up to 64 KB) may not leave room for two pipeline stages next to the epilogue's
         // staging tiles: then the tile is processed as two column slices (the operand tile is staged once per slice)
         if (ns == 2 && (NT % 32)) break;
         const size_t w_stage = w_chunk / ns;
-        for (int vb = 2; vb >= 1 && !fit; vb--) {
-            const int epi_tiles = vb + (mask ? (E->dual ? 2 : 1) : 0);
-            const size_t fixed = 4 * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 + (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0) +
-                                 sizeof(Bars2) + 1024 + 64;
-            if (fixed + 2 * (2 * (size_t)A_TILE) > (size_t)SMEM_MAX) continue;
-            const size_t budget = SMEM_MAX - fixed;
-            for (int res = 1; res >= 0 && !fit; res--) {
-                if (res && (w_total > 64 * 1024 || ns > 1)) continue;
-                const size_t stage_b = 2 * (size_t)A_TILE + (res ? 0 : w_stage);
-                if (budget < (res ? w_total : 0) + 2 * stage_b) continue;
-                int st = (int)((budget - (res ? w_total : 0)) / stage_b);
-                if (st > STAGES_MAX) st = STAGES_MAX;
-                if (res && st < 3) continue;           // residency must not starve the pipeline
-                P.stages = st; P.w_resident = res; P.v_bufs = vb; P.nsub = ns;
-                fit = true;
+        for (int ss = want_ss; ss >= 0 && !fit; ss--)
+            for (int vb = 2; vb >= 1 && !fit; vb--) {
+                const int epi_tiles = vb + (mask ? (E->dual ? 2 : 1) : 0);
+                const size_t fixed = R_EPI_WARPS * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 +
+                                     (ss ? (size_t)R_EPI_WARPS * n_stat * NT * 8 : 0) + sizeof(Bars2) + 1024 + 64;
+                if (fixed + 2 * (2 * (size_t)A_TILE) > (size_t)SMEM_MAX) continue;
+                const size_t budget = SMEM_MAX - fixed;
+                for (int res = 1; res >= 0 && !fit; res--) {
+                    if (res && (w_total > 64 * 1024 || ns > 1)) continue;
+                    const size_t stage_b = 2 * (size_t)A_TILE + (res ? 0 : w_stage);
+                    if (budget < (res ? w_total : 0) + 2 * stage_b) continue;
+                    int st = (int)((budget - (res ? w_total : 0)) / stage_b);
+                    if (st > STAGES_MAX) st = STAGES_MAX;
+                    if (res && st < 3) continue;           // residency must not starve the pipeline
+                    P.stages = st; P.w_resident = res; P.v_bufs = vb; P.nsub = ns; P.smem_stats = ss;
+                    fit = true;
+                }
             }
-        }
     }
     if (!fit) return -1;
     const int epi_tiles = P.v_bufs + (mask ? (E->dual ? 2 : 1) : 0);
     const size_t stage_b = 2 * (size_t)A_TILE + (P.w_resident ? 0 : w_chunk / P.nsub);
-    const size_t smem = (size_t)P.stages * stage_b + (P.w_resident ? w_total : 0) + 4 * (size_t)epi_tiles * 4096 + (size_t)P.n_tab * Npad * 4 +
-                        (P.smem_stats ? (size_t)4 * n_stat * NT * 8 : 0) + sizeof(Bars2) + 1024 + 64;
+    const size_t smem = (size_t)P.stages * stage_b + (P.w_resident ? w_total : 0) + R_EPI_WARPS * (size_t)epi_tiles * 4096 +
+                        (size_t)P.n_tab * Npad * 4 + (P.smem_stats ? (size_t)R_EPI_WARPS * n_stat * NT * 8 : 0) + sizeof(Bars2) + 1024 + 64;
 
     // operand pieces: columns [0, K) of the map are the operand's channels k0 .. k0 + K
     const float *p0 = A->kind == RSB_OPND_AFFINE2 ? A->U + (A->k0 % A->ku) : A->U + A->k0;
@@ -814,12 +837,14 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
 
     static bool attr_set = false;
     if (!attr_set) {
-        RSB_CUDA(cudaFuncSetAttribute(gemm_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        RSB_CUDA(cudaFuncSetAttribute(gemm_rows2_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        RSB_CUDA(cudaFuncSetAttribute(gemm_rows2_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         attr_set = true;
     }
     const long n_work = ((rows + TM - 1) / TM) * n_tiles * P.nsub;
     const int grid = (int)(n_work < rsb_sm_count() ? n_work : rsb_sm_count());
-    gemm_rows2_kernel<<<grid, THREADS2, smem, stream>>>(P);
+    if (cfg2) gemm_rows2_kernel<8, 2><<<grid, RowsCfg<8, 2>::THREADS, smem, stream>>>(P);
+    else gemm_rows2_kernel<16, 1><<<grid, RowsCfg<16, 1>::THREADS, smem, stream>>>(P);
     RSB_CHECK_LAUNCH("gemm_rows2_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;

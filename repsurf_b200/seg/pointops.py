@@ -234,6 +234,63 @@ def queryandgroup(nsample, xyz, new_xyz, feat, idx, offset, new_offset, use_xyz=
     return torch.cat((grouped_xyz, grouped_feat), -1) if use_xyz else grouped_feat
 
 
+class Subtraction(Function):
+    """ref: pointops.py:189-218.  input1 (n,c), input2 (n,c), idx (n,nsample) -> (n,nsample,c) = input1[n] - input2[idx]."""
+
+    @staticmethod
+    def forward(ctx, input1, input2, idx):
+        assert input1.is_contiguous() and input2.is_contiguous()
+        n, c = input1.shape
+        nsample = idx.shape[-1]
+        output = torch.empty(n, nsample, c, dtype=torch.float32, device=input1.device)
+        N.call("rsb_subtraction_forward", n, nsample, c, input1, input2, idx.contiguous(), output)
+        ctx.save_for_backward(idx)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        idx, = ctx.saved_tensors
+        n, nsample, c = grad_output.shape
+        grad_input1 = torch.empty(n, c, dtype=torch.float32, device=grad_output.device)
+        grad_input2 = torch.zeros(n, c, dtype=torch.float32, device=grad_output.device)
+        N.call("rsb_subtraction_backward", n, nsample, c, idx.contiguous(), grad_output.contiguous(), grad_input1, grad_input2)
+        return grad_input1, grad_input2, None
+
+
+subtraction = Subtraction.apply
+
+
+class Aggregation(Function):
+    """ref: pointops.py:221-253.  input (n,c), position (n,nsample,c), weight (n,nsample,c'), idx (n,nsample) -> (n,c):
+    sum over the samples of (input[idx] + position) * weight[..., c % c']."""
+
+    @staticmethod
+    def forward(ctx, input, position, weight, idx):
+        assert input.is_contiguous() and position.is_contiguous() and weight.is_contiguous()
+        n, nsample, c = position.shape
+        w_c = weight.shape[-1]
+        output = torch.empty(n, c, dtype=torch.float32, device=input.device)
+        N.call("rsb_aggregation_forward", n, nsample, c, w_c, input, position, weight, idx.contiguous(), output)
+        ctx.save_for_backward(input, position, weight, idx)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, position, weight, idx = ctx.saved_tensors
+        n, nsample, c = position.shape
+        w_c = weight.shape[-1]
+        dev = grad_output.device
+        grad_input = torch.zeros(n, c, dtype=torch.float32, device=dev)
+        grad_position = torch.empty(n, nsample, c, dtype=torch.float32, device=dev)
+        grad_weight = torch.empty(n, nsample, w_c, dtype=torch.float32, device=dev)
+        N.call("rsb_aggregation_backward", n, nsample, c, w_c, input, position, weight, idx.contiguous(), grad_output.contiguous(),
+               grad_input, grad_position, grad_weight)
+        return grad_input, grad_position, grad_weight, None
+
+
+aggregation = Aggregation.apply
+
+
 def _idw(dist):
     """inverse-distance weights of pointops.py:262-265 / 283-285 (un-squared distance, eps 1e-8)."""
     r = 1.0 / (dist + 1e-8)
@@ -268,5 +325,8 @@ def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
 
 
 def interpolation2(xyz, new_xyz, input, offset, new_offset, k=3):
-    """ref: pointops.py:273-307 (the autograd.Function variant; same result as `interpolation`)."""
-    return interpolation(xyz, new_xyz, input, offset, new_offset, k)
+    """ref: pointops.py:273-307 (the autograd.Function variant of `interpolation`: k nearest, inverse-distance weights,
+    gradient to `input` only)."""
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and input.is_contiguous()
+    idx, dist = knnquery(k, xyz, new_xyz, offset, new_offset)
+    return _InterpApply.apply(input, idx, _idw(dist).contiguous())

@@ -108,3 +108,44 @@ def knn_packed(nsample, xyz, new_xyz, offset, new_offset):
     lib("seg").knnquery_cuda_launcher(_i(m), _i(nsample), _p(xyz), _p(new_xyz), _p(offset), _p(new_offset), _p(idx), _p(d2))
     _sync()
     return idx, d2
+
+
+def subtraction_fwd(in1, in2, idx):
+    n, c = in1.shape
+    ns = idx.shape[1]
+    out = torch.zeros(n, ns, c, dtype=torch.float32, device=in1.device)
+    _sync()
+    lib("seg").subtraction_forward_cuda_launcher(_i(n), _i(ns), _i(c), _p(in1), _p(in2), _p(idx), _p(out))
+    _sync()
+    return out
+
+
+def subtraction_bwd(grad_out, idx):
+    n, ns, c = grad_out.shape
+    g1 = torch.zeros(n, c, dtype=torch.float32, device=grad_out.device)
+    g2 = torch.zeros(n, c, dtype=torch.float32, device=grad_out.device)
+    _sync()
+    lib("seg").subtraction_backward_cuda_launcher(_i(n), _i(ns), _i(c), _p(idx), _p(grad_out), _p(g1), _p(g2))
+    _sync()
+    return g1, g2
+
+
+def aggregation_fwd(inp, pos, w, idx):
+    n, ns, c = pos.shape
+    out = torch.zeros(n, c, dtype=torch.float32, device=inp.device)
+    _sync()
+    lib("seg").aggregation_forward_cuda_launcher(_i(n), _i(ns), _i(c), _i(w.shape[-1]), _p(inp), _p(pos), _p(w), _p(idx), _p(out))
+    _sync()
+    return out
+
+
+def aggregation_bwd(inp, pos, w, idx, grad_out):
+    n, ns, c = pos.shape
+    w_c = w.shape[-1]
+    dev = inp.device
+    g_in, g_pos, g_w = torch.zeros(n, c, device=dev), torch.zeros(n, ns, c, device=dev), torch.zeros(n, ns, w_c, device=dev)
+    _sync()
+    lib("seg").aggregation_backward_cuda_launcher(_i(n), _i(ns), _i(c), _i(w_c), _p(inp), _p(pos), _p(w), _p(idx), _p(grad_out),
+                                                  _p(g_in), _p(g_pos), _p(g_w))
+    _sync()
+    return g_in, g_pos, g_w

@@ -1,0 +1,119 @@
+"""Whole-scene inference: the kNN(32) label median filter on ONE segment of 10^6 points and the vote
+accumulation of segmentation/tool/test_s3dis.py, on the sm_100a operators."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+cuda = torch.device("cuda")
+
+
+def _room(n, seed):
+    """points on the surfaces of a 30 x 20 x 3 m room with furniture-like blobs: surface-heavy like S3DIS scans"""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(n, 3, generator=g)
+    kind = torch.randint(0, 6, (n,), generator=g)
+    p = u * torch.tensor([30.0, 20.0, 3.0])
+    p[kind == 0, 2] = 0.0                                   # floor
+    p[kind == 1, 2] = 3.0                                   # ceiling
+    p[kind == 2, 0] = 0.0                                   # walls
+    p[kind == 3, 1] = 20.0
+    blob = kind >= 4                                        # dense clusters
+    centres = torch.rand(64, 3, generator=g) * torch.tensor([30.0, 20.0, 1.5])
+    which = torch.randint(0, 64, (n,), generator=g)
+    p[blob] = centres[which[blob]] + 0.3 * torch.randn(int(blob.sum()), 3, generator=g)
+    return (p + 1e-3 * torch.randn(n, 3, generator=g)).contiguous()
+
+
+def test_grid_knn_k32_on_a_million_point_segment_matches_all_pairs():
+    """k = 32 over a single 10^6-point segment: the uniform-grid search against this package's exact all-pairs kernel
+    (10^12 candidate pairs), indices and distances bit for bit."""
+    from repsurf_b200 import _native as N
+    from repsurf_b200.seg import pointops as P
+    n, k = 1_000_000, 32
+    xyz = _room(n, 0).to(cuda)
+    off = torch.tensor([n], dtype=torch.int32, device=cuda)
+    idx, dist = P.knnquery(k, xyz, xyz, off, off)                       # grid path (n >= KNN_GRID_MIN_POINTS)
+    idx2 = torch.empty_like(idx)
+    dist2 = torch.empty_like(dist)
+    N.call("rsb_knnquery_packed", 1, n, k, xyz, xyz, off, off, idx2, dist2, 1)
+    assert torch.equal(idx, idx2) and torch.equal(dist, dist2)
+    assert bool((idx[:, 0] == torch.arange(n, device=cuda, dtype=torch.int32)).float().mean() > 0.999)   # self first (d = 0)
+
+
+def test_grid_knn_k32_matches_reference_cuda_on_one_large_segment():
+    from repsurf_b200.seg import pointops as P
+    from tests import refcuda as R
+    if not R.available("seg"):
+        pytest.skip("oracle/_ref/libref_pointops_seg.so not built")
+    n, k = 200_000, 32
+    xyz = _room(n, 1).to(cuda)
+    off = torch.tensor([n], dtype=torch.int32, device=cuda)
+    idx, dist = P.knnquery(k, xyz, xyz, off, off)
+    ridx, rd2 = R.knn_packed(k, xyz, xyz, off, off)
+    assert torch.equal(idx, ridx)
+    assert torch.equal(dist, torch.sqrt(rd2)) or float((dist - torch.sqrt(rd2)).abs().max()) < 1e-6
+
+
+def test_median_filter_matches_torch_median():
+    from repsurf_b200.seg import scene as S
+    from repsurf_b200.seg import pointops as P
+    n, k = 300_000, 32
+    xyz = _room(n, 2).to(cuda)
+    g = torch.Generator().manual_seed(3)
+    label = torch.randint(0, 13, (n,), generator=g, dtype=torch.int32).to(cuda)
+    got = S.pc_median_filter_gpu(xyz, label, k)
+    off = torch.tensor([n], dtype=torch.int32, device=cuda)
+    idx, _ = P.knnquery(k, xyz, xyz, off, off)
+    want = torch.median(label[idx.view(-1).long()].view(n, k), 1)[0].cpu().numpy()     # util/utils.py:242-244
+    assert isinstance(got, np.ndarray) and np.array_equal(got, want)
+    for kk in (1, 5, 16):                                                                # odd / even sizes
+        idx, _ = P.knnquery(kk, xyz, xyz, off, off)
+        want = torch.median(label[idx.view(-1).long()].view(n, kk), 1)[0]
+        assert torch.equal(S.label_median(xyz, label, kk), want)
+
+
+def test_vote_accumulation_and_decision():
+    from repsurf_b200.seg import scene as S
+    g = torch.Generator().manual_seed(4)
+    n, nc = 50_000, 13
+    votes = S.SceneVotes(n, nc, cuda)
+    pred = torch.zeros(n, nc, dtype=torch.float64)
+    cnt = torch.zeros(n, dtype=torch.float64)
+    for _ in range(3):
+        rows = 30_000
+        idx = torch.randperm(n, generator=g)[:rows]                    # unique inside a crop batch, as in the reference loop
+        buf = torch.randn(rows, 16, generator=g).to(cuda)              # row-padded logits (pitch 16), like the classifier head
+        logits = buf[:, :nc]
+        votes.add(logits, idx)
+        pred[idx] += torch.softmax(logits.cpu().double(), 1)
+        cnt[idx] += 1
+    assert torch.allclose(votes.pred.cpu().double(), pred, rtol=1e-5, atol=1e-6) and torch.equal(votes.count.cpu().double(), cnt)
+    seen = cnt > 0
+    got = votes.decide().cpu()
+    want = torch.argmax(votes.pred.cpu() / votes.count.cpu()[:, None], 1)
+    assert torch.equal(got[seen].long(), want[seen])
+    assert bool((got[~seen] == 0).all())                                # never-visited points: NaN rows -> class 0 (numpy.argmax)
+
+
+def test_scene_inference_loop_runs_eval_model_on_crops():
+    from repsurf_b200.models import RepSurfSeg
+    from repsurf_b200.seg import scene as S
+    from oracle.model_ref import det_fill_
+    n = 60_000
+    xyz = _room(n, 5)
+    g = torch.Generator().manual_seed(6)
+    feat = torch.rand(n, 3, generator=g)
+    model = det_fill_(RepSurfSeg()).to(cuda)
+    crops = []
+    for c in range(4):                                                  # nearest-crops of 20 000 points around 4 seeds
+        d = ((xyz - xyz[torch.randint(0, n, (1,), generator=g)]) ** 2).sum(1)
+        crops.append(torch.argsort(d)[:20_000])
+    coords = [(xyz[i] - xyz[i].mean(0)).contiguous() for i in crops]
+    feats = [feat[i].contiguous() for i in crops]
+    np.random.seed(0)
+    lab = S.scene_inference(model, coords, feats, crops, n, 13, batch_size=2, filter_k=32, coord_all=xyz)
+    assert lab.shape == (n,) and lab.dtype == torch.int32 and int(lab.min()) >= 0 and int(lab.max()) < 13
+    # a second pass reproduces the labels (eval mode: no batch statistics, no dropout; the umbrella flip is seeded)
+    np.random.seed(0)
+    assert torch.equal(S.scene_inference(model, coords, feats, crops, n, 13, batch_size=2, filter_k=32, coord_all=xyz), lab)
