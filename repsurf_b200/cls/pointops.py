@@ -207,6 +207,10 @@ def pairwise_distances(x, y=None):
     return torch.clamp(x_norm + y_norm - 2.0 * torch.mm(x, y.t()), min=0.0)
 
 
+# clouds with at least this many points go through the exact uniform-grid search (None-like: set very large to disable)
+KNN_GRID_MIN_POINTS = 4096
+
+
 class KNNQuery(Function):
     """ref: pointops.py:294-323.  -> idx (b,m,nsample) int32 sorted by (d2, index)."""
 
@@ -219,7 +223,13 @@ class KNNQuery(Function):
         b, m, _ = new_xyz.size()
         n = xyz.size(1)
         idx = torch.empty(b, m, nsample, dtype=torch.int32, device=xyz.device)
-        N.call("rsb_knnquery_dense", b, n, m, int(nsample), xyz, new_xyz, idx, None)
+        if n >= KNN_GRID_MIN_POINTS:
+            # same indices through the exact uniform-grid search (csrc/knn_grid.cu) instead of the all-pairs scan
+            nbytes = int(N.lib().rsb_knn_grid_workspace_bytes(b * n, b))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+            N.call("rsb_knnquery_grid", 0, 0, b, n, m, b * n, b * m, int(nsample), xyz, new_xyz, None, None, idx, None, 0, ws, nbytes)
+        else:
+            N.call("rsb_knnquery_dense", b, n, m, int(nsample), xyz, new_xyz, idx, None)
         ctx.mark_non_differentiable(idx)
         return idx
 
@@ -246,7 +256,12 @@ class KNNQuery_Heap(Function):
         n = xyz.size(1)
         idx = torch.empty(b, m, nsample, dtype=torch.int32, device=xyz.device)
         dist2 = torch.empty(b, m, nsample, dtype=torch.float32, device=xyz.device)
-        N.call("rsb_knnquery_heap_dense", b, n, m, int(nsample), xyz, new_xyz, idx, dist2)
+        if n >= KNN_GRID_MIN_POINTS:
+            nbytes = int(N.lib().rsb_knn_grid_workspace_bytes(b * n, b))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+            N.call("rsb_knnquery_grid", 0, 1, b, n, m, b * n, b * m, int(nsample), xyz, new_xyz, None, None, idx, dist2, 0, ws, nbytes)
+        else:
+            N.call("rsb_knnquery_heap_dense", b, n, m, int(nsample), xyz, new_xyz, idx, dist2)
         ctx.mark_non_differentiable(idx)
         return idx
 

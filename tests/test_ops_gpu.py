@@ -427,3 +427,29 @@ def test_group_rows_matches_gather_composition(polar, cf):
     if cf:
         want = torch.zeros(n, cf, dtype=torch.float64, device=cuda).index_add_(0, idx.view(-1).long(), w3[..., P4 + cn:P4 + F].reshape(-1, cf))
         assert torch.allclose(feat.grad.double(), want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("k", [9, 32])
+def test_dense_knn_large_clouds_grid_route_matches_allpairs_and_reference(k):
+    """Dense API (cls) on clouds above the grid threshold: the grid route == this package's all-pairs kernels ==
+    the reference's CUDA kernels (insertion-order and heap-order semantics), bit for bit."""
+    from repsurf_b200 import _native as N
+    from repsurf_b200.cls import pointops as P
+    from tests import refcuda as R
+    g = torch.Generator().manual_seed(77 + k)
+    b, n, m = 3, 6000, 1500
+    xyz = torch.rand(b, n, 3, generator=g).to(cuda)
+    new_xyz = xyz[:, :m].contiguous()
+    assert n >= P.KNN_GRID_MIN_POINTS
+    got = P.knnquery(k, xyz, new_xyz)
+    ap = torch.empty_like(got)
+    N.call("rsb_knnquery_dense", b, n, m, k, xyz, new_xyz, ap, None)
+    assert torch.equal(got, ap)
+    goth = P.knnquery_heap(k, xyz, new_xyz)
+    aph = torch.empty_like(goth)
+    d2 = torch.empty(b, m, k, device=cuda)
+    N.call("rsb_knnquery_heap_dense", b, n, m, k, xyz, new_xyz, aph, d2)
+    assert torch.equal(goth, aph)
+    if R.available("cls"):
+        assert torch.equal(got, R.knn_dense(k, xyz, new_xyz))
+        assert torch.equal(goth, R.knn_heap_dense(k, xyz, new_xyz)[0])
