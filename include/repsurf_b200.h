@@ -314,6 +314,29 @@ int rsb_scene_vote(long rows, int num_class, const float *logits, int ld, const 
 int rsb_scene_decide(long n, int num_class, const float *pred, const float *count, int *label, cudaStream_t stream);
 int rsb_label_median(long n, int k, const int *nbr, const int *label, int *out, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ classification evaluation harness
+ * replaces the torch-native FPS resampling of sample()            classification/modules/pointnet2_utils.py:62-75, :114-124
+ * feat [b,c,n] channel-first (xyz = channels 0..2), start [b] int64 first picks; idx [b,m] int64, out [b,c,m] = feat[:, :, idx].
+ * torch semantics: un-fused squared distance ((dx*dx + dy*dy) + dz*dz), strict-< running minimum, first-maximum picks. */
+int rsb_fps_native_sample(int b, int c, int n, int m, const float *feat, const long long *start, long long *idx, float *out,
+                          cudaStream_t stream);
+
+/* ------------------------------------------------------------------ segmentation input pipeline (grid subsampling, crop)
+ * rsb_coord_min:     out3 (pre-set to +inf) = column minima of coord [n,3]                         data_util.py:37 (coord - min)
+ * rsb_voxel_keys:    key[i] = FNV64-1A(floor((coord[i] - cmin) / voxel_size)) ^ 2^63 (signed-sortable)   voxelize_utils.py:4-17, :40
+ * rsb_voxel_runs:    runs of equal keys in the SORTED key array: start[r] = first position of run r, scalars[0] = number of
+ *                    runs (= occupied voxels); scratch = ceil(n / 1024) ints                        voxelize_utils.py:50-51 (np.unique)
+ * rsb_voxel_counts:  count[r], count_max[0] (pre-zeroed)
+ * rsb_voxel_pick:    out[r] = order[start[r] + draw[r] % count[r]]                                  voxelize_utils.py:53-55
+ * rsb_seed_distance: dist[i] = |coord[i] - coord[seed]|^2, un-fused fp32 like numpy                 data_util.py:47 */
+int rsb_coord_min(long n, const float *coord, float *out3, cudaStream_t stream);
+int rsb_voxel_keys(long n, const float *coord, const float *cmin, float voxel_size, long long *key, cudaStream_t stream);
+int rsb_voxel_runs(long n, const long long *sorted_key, int *scratch, int *start, int *scalars, cudaStream_t stream);
+int rsb_voxel_counts(int n_runs, long n, const int *start, int *count, int *count_max, cudaStream_t stream);
+int rsb_voxel_pick(int n_runs, const int *start, const int *count, const long long *draw, const long long *order,
+                   long long *out, cudaStream_t stream);
+int rsb_seed_distance(long n, const float *coord, long seed, float *dist, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

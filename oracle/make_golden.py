@@ -169,6 +169,19 @@ def golden_eval():
     print("eval golden written")
 
 
+def golden_sample():
+    """The reference's evaluation-time resampling `sample()` (classification/modules/pointnet2_utils.py:114-124, torch-native
+    FPS with a random first pick) on a seeded batch, run unmodified on the CPU."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(4, 6, 2048, generator=g) * 2 - 1
+    with RL.RefTree("cls") as t:
+        sample = t.imp("modules.pointnet2_utils").sample
+        torch.manual_seed(77)
+        out = sample(1024, x.clone())
+    np.savez_compressed(os.path.join(OUT, "cls_sample.npz"), x=_np(x), out=_np(out))
+    print("sample golden written", tuple(out.shape))
+
+
 def golden_keys():
     """state_dict keys + shapes of the UNMODIFIED reference models (checkpoint compatibility contract)."""
     import json
@@ -192,7 +205,9 @@ def golden_kat():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["cls", "seg", "segbig", "eval", "keys", "kat"]
+    which = sys.argv[1:] or ["cls", "seg", "segbig", "eval", "keys", "kat", "sample"]
+    if "sample" in which:
+        golden_sample()
     if "eval" in which:
         golden_eval()
     if "cls" in which:

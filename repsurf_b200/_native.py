@@ -41,6 +41,13 @@ _SIGS = {
     "rsb_scene_vote": [_l, _i, _p, _i, _p, _p, _p],
     "rsb_scene_decide": [_l, _i, _p, _p, _p],
     "rsb_label_median": [_l, _i, _p, _p, _p],
+    "rsb_fps_native_sample": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_coord_min": [_l, _p, _p],
+    "rsb_voxel_keys": [_l, _p, _p, _f, _p],
+    "rsb_voxel_runs": [_l, _p, _p, _p, _p],
+    "rsb_voxel_counts": [_i, _l, _p, _p, _p],
+    "rsb_voxel_pick": [_i, _p, _p, _p, _p, _p],
+    "rsb_seed_distance": [_l, _p, _l, _p],
     "rsb_sector_split": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p],
     "rsb_sector_map_back": [_i, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],

@@ -50,8 +50,12 @@ def main():
         t_ref = None
         if have_ref:
             ridx = torch.zeros(b, m, dtype=torch.int32, device=dev)
-            tmp = torch.full((b, n), 1e10, device=dev)
-            t_ref = _time(lambda: R.lib("cls").furthestsampling_cuda_launcher(_i(b), _i(n), _i(m), p(xyz), p(tmp), p(ridx)), reps=1 if n >= 32768 else 2)
+            tmp = torch.empty(b, n, device=dev)
+
+            def ref_fps():      # the reference's wrapper refills the scratch on every call (cls/po/functions/pointops.py:45)
+                tmp.fill_(1e10)
+                R.lib("cls").furthestsampling_cuda_launcher(_i(b), _i(n), _i(m), p(xyz), p(tmp), p(ridx))
+            t_ref = _time(ref_fps, reps=1 if n >= 32768 else 2)
             same = bool(torch.equal(idx, ridx))
         alg = b * ((m - 1) * n * 20 + 4 * m)
         rows.append(dict(op="fps", B=b, N=n, m=m, ms=t_us, ref_ms=t_ref, identical=same if have_ref else None,
