@@ -90,7 +90,8 @@ def data_prepare(coord, feat, label, voxel_size=0.04, voxel_max=80000, split='tr
     elif data_norm == 'min':
         coord = coord - coord.min(0)[0]
     if dataset in ('S3DIS', 'ScanNet'):
-        feat = feat / 255.
+        feat = feat / torch.tensor(255., device=feat.device)      # a tensor divisor: true division (a python scalar would
+                                                                    # become a multiplication by 1/255 on CUDA, one ulp off numpy)
         if rgb_mean is not None and rgb_std is not None:
             feat = (feat - torch.as_tensor(rgb_mean, device=feat.device, dtype=feat.dtype)) / torch.as_tensor(rgb_std, device=feat.device, dtype=feat.dtype)
     return coord.contiguous().float(), feat.contiguous().float(), (label.long() if label is not None else None)
