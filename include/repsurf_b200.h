@@ -179,6 +179,11 @@ int rsb_group_rows_forward(long rows, int ns, int polar, int P4, int Cn, int Cf,
                            cudaStream_t stream);
 int rsb_group_rows_backward(long rows, int P4, int Cn, int Cf, int ld, const float *drows, const int *idx, float *dnormal,
                             float *dfeature, cudaStream_t stream);
+/* Per-point table of a grouped level: out[i] = [xyz[i] | 0 | normal[i] | feature[i] | 0-pad], row pitch ld (multiple of 4).
+ * It is the U tensor of an RSB_OPND_GATHER operand: the first shared-MLP GEMM gathers its rows with TMA (gather4) and
+ * subtracts the group centre while staging the tile, so the [centres x nsample, C] row matrix never exists in HBM. */
+int rsb_point_table(long n, int Cn, int Cf, int ld, const float *xyz, const float *normal, const float *feature, float *out,
+                    cudaStream_t stream);
 
 /* ------------------------------------------------------------------ umbrella surface descriptors (both layouts)
  * One kernel for group_by_umbrella[_v2] + cal_normal + cal_center + xyz2sphere + cal_const + check_nan_umb
@@ -229,7 +234,11 @@ enum {
     RSB_OPND_BN_RELU = 1,       /* relu(a[k]*U[r,k] + d[k])                      previous BatchNorm + ReLU       */
     RSB_OPND_DUAL_BN_RELU = 2,  /* relu(a[k]*U[r,k]+d[k] + a[ku+k]*U[r,ku+k]+d[ku+k])   relu(bn_l(y_l)+bn_f(y_f)) */
     RSB_OPND_AFFINE2 = 3,       /* a[k]*U[r, k % ku] + b[k]*V[r,k] + d[k]        BatchNorm backward dY            */
-    RSB_OPND_POOLED = 4         /* a[k]*(arg[g,k]==r-g*ns ? U[g,k] : 0) + b[k]*V[r,k] + d[k],  g = r / ns        */
+    RSB_OPND_POOLED = 4,        /* a[k]*(arg[g,k]==r-g*ns ? U[g,k] : 0) + b[k]*V[r,k] + d[k],  g = r / ns        */
+    RSB_OPND_GATHER = 5         /* U[arg[r], k] - (k < 3 ? V[r / ns, k] : 0): the grouped level's row matrix built while the
+                                   tile is staged - U = per-point table [ku rows, ldu] = [xyz, 0 | normal, feature | 0-pad],
+                                   arg = neighbour index of every row, V = group centres [rows/ns, 3]  (TMA gather4; replaces
+                                   the gathers + subtraction + cat of seg/modules/repsurface_utils.py:36-49)               */
 };
 typedef struct {
     const float *U, *V;      /* U: [rows, ldu] (POOLED: [rows/ns, ldu] pooled gradient), V: [rows, ldv]            */
@@ -256,6 +265,8 @@ typedef struct {
     int ldl;
     const float *sc, *sh, *mu, *inv;
     int kind, dual;
+    const int *scatter;      /* BIAS_STATS without bias/stats: Y[scatter[r], :] += acc[r, :] (vector reductions) instead of
+                                Y[r, :] = acc - the grouping backward fused into the input-gradient GEMM, or NULL         */
 } rsb_epi_t;
 
 /* Kernel generation of rsb_gemm_rows / rsb_gemm_wgrad: 0 (default) = the TMA-fed kernels (csrc/mlp_tc2.cu) whenever

@@ -48,6 +48,7 @@ _SIGS = {
     "rsb_voxel_counts": [_i, _l, _p, _p, _p],
     "rsb_voxel_pick": [_i, _p, _p, _p, _p, _p],
     "rsb_seed_distance": [_l, _p, _l, _p],
+    "rsb_point_table": [_l, _i, _i, _i, _p, _p, _p, _p],
     "rsb_sector_split": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p],
     "rsb_sector_map_back": [_i, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],

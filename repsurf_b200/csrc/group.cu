@@ -201,6 +201,24 @@ __global__ void __launch_bounds__(TPB) group_rows_fwd(long rows, int ns, int pol
     }
 }
 
+// per-point table of a level, the source of the gathered first-layer operand (RSB_OPND_GATHER):
+//   out[i, :] = [ xyz[i] (3) | 0 | normal[i, :Cn] | feature[i, :Cf] | 0-pad to ld ]      (ld % 4 == 0: 16-byte rows for TMA)
+__global__ void __launch_bounds__(TPB) point_table_kernel(long n, int Cn, int Cf, int ld, const float *__restrict__ xyz,
+                                                          const float *__restrict__ normal, const float *__restrict__ feature,
+                                                          float *__restrict__ out)
+{
+    const long total = n * ld;
+    for (long i = blockIdx.x * (long)TPB + threadIdx.x; i < total; i += (long)gridDim.x * TPB) {
+        const long r = rsb_div(i, ld);
+        const int c = (int)(i - r * ld);
+        float v = 0.f;
+        if (c < 3) v = __ldg(xyz + r * 3 + c);
+        else if (c >= 4 && c < 4 + Cn) v = __ldg(normal + r * Cn + (c - 4));
+        else if (c >= 4 + Cn && c < 4 + Cn + Cf) v = __ldg(feature + r * Cf + (c - 4 - Cn));
+        out[i] = v;
+    }
+}
+
 // scatter-add of the feature columns of d(rows) back to the per-point tensors (fp32 atomics, like the reference's
 // grouping backward: order-dependent sums, rule R6)
 __global__ void __launch_bounds__(TPB) group_rows_bwd(long rows, int P4, int Cn, int Cf, int ld, const float *__restrict__ drows,
@@ -317,6 +335,14 @@ RSB_EXPORT int rsb_group_rows_forward(long rows, int ns, int polar, int P4, int 
 {
     RSB_REQUIRE(P4 >= (polar ? 6 : 3) && ld >= P4 + Cn + Cf, "bad column layout");
     RSB_LAUNCH_1D(group_rows_fwd, rows * ld, rows, ns, polar, P4, Cn, Cf, ld, xyz, new_xyz, idx, normal, feature, out);
+    return 0;
+}
+
+RSB_EXPORT int rsb_point_table(long n, int Cn, int Cf, int ld, const float *xyz, const float *normal, const float *feature,
+                               float *out, cudaStream_t stream)
+{
+    RSB_REQUIRE(ld % 4 == 0 && ld >= 4 + Cn + Cf && (Cn == 0 || normal) && (Cf == 0 || feature), "bad column layout");
+    RSB_LAUNCH_1D(point_table_kernel, n * ld, n, Cn, Cf, ld, xyz, normal, feature, out);
     return 0;
 }
 

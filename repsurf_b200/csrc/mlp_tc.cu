@@ -1192,7 +1192,8 @@ inline int pick_nt(int N) { const int t = (N + NT_MAX - 1) / NT_MAX; return roun
 
 int check_opnd(const Opnd &O, const char *what)
 {
-    if (O.K < 1 || O.kind < 0 || O.kind > RSB_OPND_POOLED) { rsb_set_error("%s: bad operand descriptor", what); return 1; }
+    if (O.K < 1 || O.kind < 0 || O.kind > RSB_OPND_GATHER) { rsb_set_error("%s: bad operand descriptor", what); return 1; }
+    if (O.kind == RSB_OPND_GATHER) return 0;    // checked by the TMA-fed launcher, the only implementation
     if (!O.U) { rsb_set_error("%s: operand U is null", what); return 1; }
     if (O.kind != RSB_OPND_RAW && (!O.a || !O.d)) { rsb_set_error("%s: operand needs coefficient vectors", what); return 1; }
     if ((O.kind == RSB_OPND_AFFINE2 || O.kind == RSB_OPND_POOLED) && (!O.V || !O.b || O.ku < 1)) { rsb_set_error("%s: affine operand needs V, b, ku", what); return 1; }
@@ -1236,6 +1237,10 @@ RSB_EXPORT int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float 
     {   // TMA-fed kernel (mlp_tc2.cu) whenever the operands meet its alignment rules
         const int r2 = rsb_gemm_rows2_launch(rows, N, A, Wp, E, stream);
         if (r2 >= 0) return r2;
+        if (A->kind == RSB_OPND_GATHER || E->scatter) {
+            rsb_set_error("rsb_gemm_rows: gathered operands / scattered results need the TMA-fed kernel (16-byte aligned table, pitch %% 4 == 0)");
+            return (int)cudaErrorInvalidValue;
+        }
         if (g_tc_trace)
             fprintf(stderr, "[rsb] gemm_rows -> first-generation kernel: rows %ld N %d K %d kind %d k0 %d ku %d ldu %d ldv %d ldy %d epi %d\n", rows, N,
                     A->K, A->kind, A->k0, A->ku, A->ldu, A->ldv, E->ldy, E->kind);
@@ -1284,6 +1289,10 @@ RSB_EXPORT int rsb_gemm_wgrad(long rows, const rsb_opnd_t *G, const rsb_opnd_t *
     {
         const int r2 = rsb_gemm_wgrad2_launch(rows, G, X, dW, ldw, stream);
         if (r2 >= 0) return r2;
+        if (G->kind == RSB_OPND_GATHER || X->kind == RSB_OPND_GATHER) {
+            rsb_set_error("rsb_gemm_wgrad: gathered operands need the TMA-fed kernel (16-byte aligned table, pitch %% 4 == 0)");
+            return (int)cudaErrorInvalidValue;
+        }
         if (g_tc_trace)
             fprintf(stderr, "[rsb] gemm_wgrad -> first-generation kernel: rows %ld G(K %d kind %d k0 %d ku %d ldu %d ldv %d) X(K %d kind %d k0 %d ku %d ldu %d ldv %d)\n",
                     rows, G->K, G->kind, G->k0, G->ku, G->ldu, G->ldv, X->K, X->kind, X->k0, X->ku, X->ldu, X->ldv);

@@ -129,6 +129,7 @@ __device__ __forceinline__ float4 xform(int kind, const float4 u, const float4 w
     float4 v;
     switch (kind) {
     case RSB_OPND_RAW:
+    case RSB_OPND_GATHER:      // the centre subtraction of columns 0..2 happens in the transform loop (it needs the row)
         v = u;
         break;
     case RSB_OPND_BN_RELU:
@@ -195,7 +196,9 @@ struct Rows2Params {
     long rows;
     int N, NT, n_tiles, k_chunks, stages;
     int nsub;         // an N tile is processed as nsub column slices of NT / nsub (when a full tile's weights do not fit a stage)
-    int n_pieces;     // raw tensors behind the operand (1: RAW / BN_RELU, 2: DUAL / AFFINE2)
+    int n_pieces;     // raw tensors behind the operand (1: RAW / BN_RELU / GATHER, 2: DUAL / AFFINE2)
+    int gather;       // operand rows are gathered by index (TMA gather4) and centred
+    int scatter;      // epilogue adds the rows into Y[scatter[r]] instead of storing Y[r]
     int w_resident;   // the pre-split weights of all (N tile, K chunk) pairs stay in shared memory
     int v_bufs;       // staging tiles per epilogue warp for the outgoing block (1 or 2)
     int n_tab;        // per-column epilogue tables in shared memory (bias | sc, sh, mu [, second half])
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(RowsCfg<XFW, ES>::THREADS, 1) gemm_rows2_kerne
         const bool zero_lo = !two && KCH > 1;       // stale "lo" data of a full chunk under an invalid quad of the last chunk
         uint32_t it = 0;
         for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const long tile_row0 = (w / per_tile) * TM;
             for (int kc = 0; kc < KCH; kc++, it++) {
                 const int s = it % S;
                 if (!hoist) {
@@ -294,6 +298,20 @@ __global__ void __launch_bounds__(RowsCfg<XFW, ES>::THREADS, 1) gemm_rows2_kerne
                     for (int j = 0; j < R_XF_PIECES; j++) {
                         u[j] = lds128(a0 + j * (R_XF_THREADS * 16));
                         x[j] = two ? lds128(a0 + A_TILE + j * (R_XF_THREADS * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (P.gather && kc == 0 && q == 0) {
+                        // columns 0..2 of a gathered row are the neighbour's coordinates: make them relative to the group centre
+                        // (same subtraction, same rounding as the row builder group_rows_fwd)
+#pragma unroll
+                        for (int j = 0; j < R_XF_PIECES; j++) {
+                            const long r = tile_row0 + (tid >> 3) + j * (R_XF_THREADS / 8);
+                            if (r < P.rows) {
+                                const float *cen = A.V + (r / A.ns) * 3;
+                                u[j].x = __fsub_rn(u[j].x, __ldg(cen));
+                                u[j].y = __fsub_rn(u[j].y, __ldg(cen + 1));
+                                u[j].z = __fsub_rn(u[j].z, __ldg(cen + 2));
+                            }
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < R_XF_PIECES; j++) {
@@ -312,7 +330,38 @@ __global__ void __launch_bounds__(RowsCfg<XFW, ES>::THREADS, 1) gemm_rows2_kerne
         }
     } else if (warp == R_LOAD_WARP) {
         // =============================== TMA issuer ===============================
-        if (lane == 0) {
+        if (P.gather) {
+            // every lane gathers 4 of the tile's 128 rows per K chunk: 32 gather4 instructions fill the same SWIZZLE_128B tile
+            // a plain box load would (each lands on 4 consecutive 128-byte lines)
+            if (lane == 0 && P.w_resident) {
+                mbar_arrive_expect_tx(&B->w_bar, w_res_bytes);
+                bulk_g2s(w_res, P.Wp, w_res_bytes, &B->w_bar);
+            }
+            uint32_t it = 0;
+            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const long tile = w / per_tile;
+                const int rem = (int)(w - tile * per_tile);
+                const int nt = rem / NS, sub = rem - nt * NS;
+                const long r0 = tile * TM + 4 * lane;
+                int id[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) id[e] = __ldg(A.arg + min(r0 + e, P.rows - 1));
+                for (int kc = 0; kc < KCH; kc++, it++) {
+                    const int s = it % S;
+                    mbar_wait(&B->empty[s], ((it / S) & 1) ^ 1);
+                    const uint32_t st = base + (uint32_t)s * stage_bytes;
+                    if (lane == 0) mbar_arrive_expect_tx(&B->raw_full[s], A_TILE);
+                    __syncwarp();
+                    tma_gather4(st + (uint32_t)lane * 512u, &P.mapA0, kc * KC, id[0], id[1], id[2], id[3], &B->raw_full[s]);
+                    if (lane == 0 && !P.w_resident) {
+                        const float *wc = P.Wp + ((size_t)nt * KCH + kc) * (2 * (size_t)NT * KC) + (size_t)sub * NTs * KC;
+                        mbar_arrive_expect_tx(&B->full[s], 2u * w_slice);
+                        bulk_g2s(st + 2 * A_TILE, wc, w_slice, &B->full[s]);
+                        bulk_g2s(st + 2 * A_TILE + w_slice, wc + (size_t)NT * KC, w_slice, &B->full[s]);
+                    }
+                }
+            }
+        } else if (lane == 0) {
             if (P.w_resident) {
                 mbar_arrive_expect_tx(&B->w_bar, w_res_bytes);
                 bulk_g2s(w_res, P.Wp, w_res_bytes, &B->w_bar);
@@ -413,7 +462,18 @@ __global__ void __launch_bounds__(RowsCfg<XFW, ES>::THREADS, 1) gemm_rows2_kerne
                     __syncwarp();
                 }
                 const uint32_t vt = my_epi + (vb % (uint32_t)P.v_bufs) * 4096u + my_row_off;
-                if (!mask) {
+                if (P.scatter) {
+                    // grouping backward fused into the input-gradient GEMM: row r adds its 32-column block to row scatter[r] of
+                    // the per-point gradient table (columns >= N carry zeros: the weight tile is zero-padded)
+                    if (row_ok) {
+                        float *dst = E.Y + (size_t)__ldg(E.scatter + row) * E.ldy + nl;
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            if (nl + 4 * c < P.N)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                                             "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+                    }
+                } else if (!mask) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(t_bias + nl + 4 * c);
@@ -546,6 +606,7 @@ struct Wgrad2Params {
     long rows;
     int M, N, NT, NTB, m_tiles, n_tiles, splits, stages;
     int g_pieces, x_pieces;
+    int x_gather;     // X rows are gathered by index (TMA gather4) and centred (RSB_OPND_GATHER)
 };
 
 // first column (in the piece's tensor map) of the 32-channel box that starts at logical channel c of operand O
@@ -652,8 +713,13 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
                     c.d = *reinterpret_cast<const float4 *>(ctab + 2 * TABW + ch);
                     c.a2 = *reinterpret_cast<const float4 *>(ctab + 3 * TABW + ch);
                     c.d2 = *reinterpret_cast<const float4 *>(ctab + 4 * TABW + ch);
-                    const float4 u = lds128(addr);
+                    float4 u = lds128(addr);
                     const float4 x = x2 ? lds128(addr + x_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (P.x_gather && nt == 0 && bx == 0 && q == 0 && row_ok) {
+                        // gathered rows: neighbour coordinates -> relative to the group centre (columns 0..2)
+                        const float *cen = P.X.V + (((c_begin + ci) * KC + kr) / P.X.ns) * 3;
+                        u.x = __fsub_rn(u.x, __ldg(cen)); u.y = __fsub_rn(u.y, __ldg(cen + 1)); u.z = __fsub_rn(u.z, __ldg(cen + 2));
+                    }
                     float4 v = xform(P.X.kind, u, x, c);
                     if (!row_ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 hi, lo;
@@ -666,7 +732,34 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
             }
         } else if (warp == LOAD_WARP) {
             // =============================== TMA issuer ===============================
-            if (lane == 0) {
+            if (P.x_gather) {
+                // G boxes by lane 0; the X boxes (32 rows x 32 channels each) by gather4: lane l fetches rows 4 (l % 8) .. + 3 of the
+                // chunk for box l / 8, then lanes + 32 ... until all xb boxes are issued
+                const uint32_t tx = (uint32_t)(P.g_pieces * gb + xb) * BOX;
+                uint32_t it = 0;
+                for (long ci = 0; ci < my_chunks; ci++, it++) {
+                    const int s = it % S;
+                    mbar_wait(&B->empty[s], ((it / S) & 1) ^ 1);
+                    const uint32_t st = base + (uint32_t)s * stage_bytes;
+                    const int row0 = (int)((c_begin + ci) * KC);
+                    const int g4 = lane & 7;
+                    int id[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) id[e] = __ldg(P.X.arg + min((long)row0 + 4 * g4 + e, P.rows - 1));
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&B->raw_full[s], tx);
+                        for (int g = 0; g < gb; g++) {
+                            const int c = mt * TM + g * 32;
+                            tma_load_2d(st + (uint32_t)g * BOX, &P.mapG0, piece0_col(P.G, c), row0, &B->raw_full[s]);
+                            if (P.g_pieces == 2) tma_load_2d(st + A_TILE + (uint32_t)g * BOX, &P.mapG1, P.G.k0 + c, row0, &B->raw_full[s]);
+                        }
+                    }
+                    __syncwarp();
+                    for (int x = lane >> 3; x < xb; x += 4)
+                        tma_gather4(st + 2 * A_TILE + (uint32_t)x * BOX + (uint32_t)g4 * 512u, &P.mapX0, nt * NT + x * 32, id[0], id[1], id[2], id[3],
+                                    &B->raw_full[s]);
+                }
+            } else if (lane == 0) {
                 const uint32_t tx = (uint32_t)(P.g_pieces * gb + P.x_pieces * xb) * BOX;
                 uint32_t it = 0;
                 for (long ci = 0; ci < my_chunks; ci++, it++) {
@@ -750,6 +843,7 @@ int g_force_v1 = [] { const char *v = getenv("RSB_TC_V1"); return (v && v[0] && 
 bool opnd_tma_ok(const Opnd &O)
 {
     if (O.kind == RSB_OPND_POOLED) return false;
+    if (O.kind == RSB_OPND_GATHER) return al16(O.U) && (O.ldu & 3) == 0 && O.k0 == 0 && O.arg && O.V && O.ns >= 1 && O.ku >= 1;
     if (!al16(O.U) || (O.ldu & 3) || (O.k0 & 3)) return false;
     if (O.kind == RSB_OPND_DUAL_BN_RELU && (O.ku & 3)) return false;
     if (O.kind == RSB_OPND_AFFINE2 && (!al16(O.V) || (O.ldv & 3) || (O.ku & 3))) return false;
@@ -770,6 +864,7 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
     if (A->kind == RSB_OPND_AFFINE2 && (A->k0 % A->ku) + A->K > A->ku) return -1;     // U would wrap inside the operand
     const bool mask = E->kind == RSB_EPI_RELU_MASK;
     if (E->Y && (!al16(E->Y) || (E->ldy & 3))) return -1;
+    if (E->scatter && (mask || E->bias || E->stats || !E->Y)) return -1;
     if (mask && (!al16(E->Yl) || (E->ldl & 3) || (N & 3))) return -1;
     // same tiling rule as pick_nt() in mlp_tc.cu, which laid out the pre-split weight buffer
     const int nt0 = (N + 255) / 256;
@@ -781,7 +876,9 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
     P.A = *A; P.E = *E; P.Wp = Wp; P.rows = rows; P.N = N; P.NT = NT; P.n_tiles = n_tiles;
     P.k_chunks = (A->K + KC - 1) / KC;
     P.n_pieces = (A->kind == RSB_OPND_DUAL_BN_RELU || A->kind == RSB_OPND_AFFINE2) ? 2 : 1;
-    P.has_y = E->Y != nullptr;
+    P.gather = A->kind == RSB_OPND_GATHER ? 1 : 0;
+    P.scatter = E->scatter ? 1 : 0;
+    P.has_y = E->Y != nullptr && !P.scatter;
     P.n_tab = mask ? (E->dual ? 6 : 3) : 1;
     P.smem_stats = (E->stats && n_tiles == 1) ? 1 : 0;
     const int n_stat = mask ? (E->dual ? 3 : 2) : 2;
@@ -827,7 +924,9 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
 
     // operand pieces: columns [0, K) of the map are the operand's channels k0 .. k0 + K
     const float *p0 = A->kind == RSB_OPND_AFFINE2 ? A->U + (A->k0 % A->ku) : A->U + A->k0;
-    if (make_map(&P.mapA0, p0, A->K, rows, A->ldu, KC, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return (int)cudaErrorInvalidValue;
+    if (P.gather) {     // gather4 wants a one-row box; the table has ku rows
+        if (make_map(&P.mapA0, A->U, A->K, A->ku, A->ldu, KC, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return (int)cudaErrorInvalidValue;
+    } else if (make_map(&P.mapA0, p0, A->K, rows, A->ldu, KC, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return (int)cudaErrorInvalidValue;
     if (P.n_pieces == 2) {
         const float *p1 = A->kind == RSB_OPND_DUAL_BN_RELU ? A->U + A->ku + A->k0 : A->V + A->k0;
         const long ld1 = A->kind == RSB_OPND_DUAL_BN_RELU ? A->ldu : A->ldv;
@@ -854,6 +953,7 @@ int rsb_gemm_wgrad2_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, 
 {
     if (g_force_v1 || !encoder()) return -1;
     if (!opnd_tma_ok(*G) || !opnd_tma_ok(*X)) return -1;
+    if (G->kind == RSB_OPND_GATHER) return -1;           // only the X operand (the layer's input rows) is ever gathered
     if (rows + KC >= (1L << 31)) return -1;
     // AFFINE2 operands whose U tensor wraps (k % ku) inside the operand: every 32-channel box must stay inside one period
     auto wrap_ok = [](const Opnd &O) {
@@ -894,7 +994,10 @@ int rsb_gemm_wgrad2_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, 
     P.splits = (int)splits;
 
     // piece maps: the column coordinate is the stored tensor's own column index (see piece0_col)
+    P.x_gather = X->kind == RSB_OPND_GATHER ? 1 : 0;
     auto maps = [&](const Opnd &O, CUtensorMap *m0, CUtensorMap *m1) {
+        if (O.kind == RSB_OPND_GATHER)      // one-row box for gather4 over the per-point table (ku rows)
+            return make_map(m0, O.U, O.K, O.ku, O.ldu, 32, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         const long ext0 = O.kind == RSB_OPND_AFFINE2 ? O.ku : (long)O.k0 + O.K;
         if (make_map(m0, O.U, ext0, rows, O.ldu, 32, KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
         if (O.kind == RSB_OPND_DUAL_BN_RELU)

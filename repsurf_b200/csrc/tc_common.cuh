@@ -60,6 +60,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                  "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(rsb_smem_addr(bar))
                  : "memory");
 }
+// four rows r0..r3 of a 2-D tensor (tensor map with a ONE-row box of `box cols` columns starting at column c0) -> four
+// consecutive box rows at dst; with SWIZZLE_128B the 16-byte chunks are XOR-ed with the shared-memory line index exactly as a
+// plain tile load does (hardware probe: scripts/gather4_probe.cu, profiles/r02_gather4_probe.txt)
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *map, int c0, int r0, int r1, int r2, int r3, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(rsb_smem_addr(bar))
+                 : "memory");
+}
 // 2-D tensor tile shared -> global (clipped to the tensor-map extents), bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src)
 {

@@ -54,10 +54,52 @@ def group_rows(xyz, new_xyz, idx, normal, feature, nsample, polar):
     return rows, (P4, (normal.shape[1] if normal is not None else 0) + (feature.shape[1] if feature is not None else 0))
 
 
+class _PointTable(torch.autograd.Function):
+    """[xyz | 0 | normal | feature | 0-pad] per POINT (csrc/group.cu point_table_kernel): the table the first shared-MLP GEMM
+    gathers its rows from.  Backward: the GEMM's scatter epilogue has already summed the row gradients per point."""
+
+    @staticmethod
+    def forward(ctx, xyz, normal, feature):
+        from . import _native as N
+        n = xyz.shape[0]
+        Cn = normal.shape[1] if normal is not None else 0
+        Cf = feature.shape[1] if feature is not None else 0
+        ld = 4 + (Cn + Cf + 3) // 4 * 4
+        out = torch.empty(n, ld, device=xyz.device)
+        N.call("rsb_point_table", n, Cn, Cf, ld, xyz.contiguous(), None if normal is None else normal.contiguous(),
+               None if feature is None else feature.contiguous(), out)
+        ctx.dims = (Cn, Cf)
+        return out
+
+    @staticmethod
+    def backward(ctx, dT):
+        Cn, Cf = ctx.dims
+        dn = dT[:, 4:4 + Cn].contiguous() if (Cn and ctx.needs_input_grad[1]) else None
+        df = dT[:, 4 + Cn:4 + Cn + Cf].contiguous() if (Cf and ctx.needs_input_grad[2]) else None
+        return None, dn, df
+
+
+class GatheredRows:
+    """The row matrix of a grouped level, NOT materialised: rows[r] = table[idx[r]] with the first three columns made
+    relative to centres[r // nsample].  The first-layer GEMMs (forward, weight gradient) gather it tile by tile with TMA
+    and the input-gradient GEMM scatters into the table's gradient (repsurf_b200.tc, RSB_OPND_GATHER)."""
+
+    def __init__(self, table, idx, centres, nsample, layout):
+        self.table, self.idx, self.centres, self.nsample, self.layout = table, idx, centres, nsample, layout
+
+
+def gather_rows(xyz, new_xyz, idx, normal, feature, nsample):
+    """Fused form of group_rows for levels without the polar columns: returns a GatheredRows (layout: position columns
+    0..2 (+ zero pad), features from column 4)."""
+    table = _PointTable.apply(xyz, normal, feature)
+    F_ = (normal.shape[1] if normal is not None else 0) + (feature.shape[1] if feature is not None else 0)
+    return GatheredRows(table, idx.reshape(-1).contiguous(), new_xyz.contiguous(), nsample, (4, F_))
+
+
 def sa_mlp(rows, pos_channel, mod, nsample, layout=None):
     """Shared MLP + max-pool of a SurfaceAbstractionCD level: the fused tcgen05 path of repsurf_b200.tc (3xTF32 GEMMs with
     BatchNorm / ReLU / pool folded into operand loads and epilogues, hand-written backward) in training AND eval mode."""
-    if not rows.is_cuda:
+    if not (rows.table if isinstance(rows, GatheredRows) else rows).is_cuda:
         raise RuntimeError("repsurf_b200 has no CPU path")
     if len(mod.mlp_convs) < 1:
         raise RuntimeError("the fused shared MLP needs at least two layers (mlp = [c0, c1, ...])")

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from . import pointops as P
 from .. import _native as N
 from .. import tc
-from ..mlp import group_rows, sa_mlp
+from ..mlp import gather_rows, group_rows, sa_mlp
 
 
 def strided_offsets(offset, stride):
@@ -42,6 +42,8 @@ def strided_offsets(offset, stride):
 # an active plan they compute everything themselves, in order, on the current stream (same results either way).
 # ---------------------------------------------------------------------------------------------------------------
 _ACTIVE_PLAN = None
+# first shared-MLP layer reads its rows through a TMA gather instead of a materialised row matrix (levels without polar columns)
+FUSE_GATHER = True
 _SIDE_STREAMS = {}
 
 
@@ -151,6 +153,10 @@ def _sample_and_group(stride, nsample, center, normal, feature, offset, return_p
             fps_idx, new_center, new_offset = None, center, offset
         group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
     new_normal = normal[fps_idx, :] if fps_idx is not None else normal
+    if not return_polar and FUSE_GATHER:
+        # the row matrix is never built: the first GEMMs gather [xyz | normal | feature] rows of a per-point table with TMA
+        rows = gather_rows(center, new_center, group_idx, normal, feature, nsample)
+        return new_center, new_normal, rows, rows.layout, new_offset
     rows, layout = group_rows(center, new_center, group_idx, normal, feature, nsample, return_polar)
     return new_center, new_normal, rows, layout, new_offset
 

@@ -10,7 +10,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _native as N
 
-OPND_RAW, OPND_BN_RELU, OPND_DUAL, OPND_AFFINE2, OPND_POOLED = 0, 1, 2, 3, 4
+OPND_RAW, OPND_BN_RELU, OPND_DUAL, OPND_AFFINE2, OPND_POOLED, OPND_GATHER = 0, 1, 2, 3, 4, 5
 EPI_BIAS_STATS, EPI_RELU_MASK = 0, 1
 
 
@@ -24,7 +24,8 @@ class Opnd(ctypes.Structure):
 class Epi(ctypes.Structure):
     _fields_ = [("Y", ctypes.c_void_p), ("ldy", ctypes.c_int), ("bias", ctypes.c_void_p), ("stats", ctypes.c_void_p),
                 ("Yl", ctypes.c_void_p), ("ldl", ctypes.c_int), ("sc", ctypes.c_void_p), ("sh", ctypes.c_void_p),
-                ("mu", ctypes.c_void_p), ("inv", ctypes.c_void_p), ("kind", ctypes.c_int), ("dual", ctypes.c_int)]
+                ("mu", ctypes.c_void_p), ("inv", ctypes.c_void_p), ("kind", ctypes.c_int), ("dual", ctypes.c_int),
+                ("scatter", ctypes.c_void_p)]
 
 
 def _dp(t, off=0):
@@ -53,9 +54,11 @@ def prep_weight(W, transposed=False):
     return buf, Nn, K
 
 
-def gemm_rows(rows, Nn, A, Wp, Y=None, ldy=None, y_off=0, bias=None, stats=None, mask=None):
-    """Y[:, y_off:y_off+N] = A @ W^T (+bias) ; mask = (Yl, sc, sh, mu, inv, dual) selects the dgrad epilogue."""
+def gemm_rows(rows, Nn, A, Wp, Y=None, ldy=None, y_off=0, bias=None, stats=None, mask=None, scatter=None):
+    """Y[:, y_off:y_off+N] = A @ W^T (+bias) ; mask = (Yl, sc, sh, mu, inv, dual) selects the dgrad epilogue;
+    scatter = int32 [rows]: Y[scatter[r], y_off:] += row r instead (grouping backward fused into the GEMM)."""
     e = Epi()
+    e.scatter = None if scatter is None else scatter.data_ptr()
     e.Y = _dp(Y, y_off)
     e.ldy = (Y.stride(0) if ldy is None else ldy) if Y is not None else 0
     e.bias, e.stats = _dp(bias), (None if stats is None else stats.data_ptr())
@@ -121,7 +124,9 @@ class _FusedSAMLP(Function):
         frozen = meta["frozen"]          # BatchNorm layers normalise with their running statistics (eval / frozen)
         bns = meta["bns"]
         dev = X.device
-        R, Cin = X.shape
+        gat = meta.get("gather")            # (idx int32 [R], centres [G, 3]): X is the per-point table, rows are gathered by TMA
+        Cin = X.shape[1]
+        R = gat[0].numel() if gat is not None else X.shape[0]
         G = R // ns
         W_l, b_l, W_f, b_f, g_l, be_l, g_f, be_f = params[:8]
         C0 = W_l.shape[0]
@@ -142,7 +147,8 @@ class _FusedSAMLP(Function):
             stbuf = torch.zeros(sum(widths), dtype=torch.float64, device=dev)
             stats_of = list(torch.split(stbuf, widths))
         st = stats_of[0]
-        gemm_rows(R, 2 * C0, opnd(OPND_RAW, X, Cin), Wp0, Y=Y0, bias=bias0, stats=st)
+        A0 = opnd(OPND_RAW, X, Cin) if gat is None else opnd(OPND_GATHER, X, Cin, V=gat[1], arg=gat[0], ku=X.shape[0], ns=ns)
+        gemm_rows(R, 2 * C0, A0, Wp0, Y=Y0, bias=bias0, stats=st)
         if frozen:
             coefs = [_bn_eval_coef(bns[:2])]
         else:
@@ -192,7 +198,9 @@ class _FusedSAMLP(Function):
         fz = 2 if meta["frozen"] else 0
         X, Wbd, Ws, Ys, coefs, arg = ctx.saved
         dev = X.device
-        R, Cin = X.shape
+        gat = meta.get("gather")
+        Cin = X.shape[1]
+        R = gat[0].numel() if gat is not None else X.shape[0]
         G = R // ns
         C0 = Wbd.shape[0] // 2
         L = n_extra  # index of the last layer (0 = block-diagonal first layer)
@@ -249,15 +257,17 @@ class _FusedSAMLP(Function):
             dZ0, cop0 = dZ, cop
         # ---- first layer: weight gradient of the block-diagonal GEMM, input gradient of the feature columns
         dWbd = dw_parts.pop(0).view(2 * C0, Cin)
-        gemm_wgrad(R, Gop, opnd(OPND_RAW, X, Cin), dWbd)
+        X0 = opnd(OPND_RAW, X, Cin) if gat is None else opnd(OPND_GATHER, X, Cin, V=gat[1], arg=gat[0], ku=X.shape[0], ns=ns)
+        gemm_wgrad(R, Gop, X0, dWbd)
         dX = None
         P4, F = meta["feat_col"], meta["feat_channels"]
         if ctx.needs_input_grad[0]:
-            dX = torch.zeros(R, Cin, device=dev)
+            dX = torch.zeros(X.shape[0], Cin, device=dev)
             Wf = Wbd[C0:, P4:P4 + F].contiguous()            # [C0, F]
             WpT, _, _ = prep_weight(Wf, transposed=True)     # operand [N=F, K=C0]
             Gf = opnd(OPND_AFFINE2, dZ0, C0, a=cop0[0], b=cop0[1], d=cop0[2], V=Ys[0], ku=C0, k0=C0)
-            gemm_rows(R, F, Gf, WpT, Y=dX, ldy=Cin, y_off=P4)
+            # gathered rows: the gradient of row r goes to the table row it was gathered from (scatter fused into the GEMM)
+            gemm_rows(R, F, Gf, WpT, Y=dX, ldy=Cin, y_off=P4, scatter=None if gat is None else gat[0])
         # ---- assemble parameter gradients in the order of *params
         W_l_shape, W_f_shape = meta["W_l_shape"], meta["W_f_shape"]
         # biases in front of a train-mode BatchNorm have an exactly zero gradient: slices of one zero buffer
@@ -306,8 +316,14 @@ def sa_mlp_fused(rows, pos_channel, mod, nsample, layout=None):
               mod.bn_l0.weight, mod.bn_l0.bias, mod.bn_f0.weight, mod.bn_f0.bias]
     for lin, bn in zip(mod.mlp_convs, mod.mlp_bns):
         params += [lin.weight, lin.bias, bn.weight, bn.bias]
+    gather = None
+    if hasattr(rows, "table"):              # mlp.GatheredRows: the row matrix exists only as (table, neighbour index, centres)
+        gather, layout, n_rows = (rows.idx, rows.centres), rows.layout, rows.idx.numel()
+        rows = rows.table
+    else:
+        n_rows = rows.shape[0]
     feat_col, feat_channels = layout if layout is not None else (pos_channel, rows.shape[1] - pos_channel)
-    meta = dict(ns=nsample, pos_channel=pos_channel, feat_col=feat_col, feat_channels=feat_channels,
+    meta = dict(ns=nsample, pos_channel=pos_channel, feat_col=feat_col, feat_channels=feat_channels, gather=gather,
                 eps=mod.bn_l0.eps, n_extra=len(mod.mlp_convs), frozen=frozen, bns=bns,
                 W_l_shape=tuple(mod.mlp_l0.weight.shape), W_f_shape=tuple(mod.mlp_f0.weight.shape),
                 W_shapes=[tuple(l.weight.shape) for l in mod.mlp_convs])
@@ -316,7 +332,7 @@ def sa_mlp_fused(rows, pos_channel, mod, nsample, layout=None):
     if frozen:
         return out
     # running statistics (same side effects as the BatchNorm modules): batch mean, UNBIASED batch variance
-    R = rows.shape[0]
+    R = n_rows
     with torch.no_grad():
         C0 = mod.mlp_l0.weight.shape[0]
         st0 = stats[0]                                       # [sum l | sum f | sumsq l | sumsq f]

@@ -242,3 +242,37 @@ def test_umbrella_mlp_fused_matches_fp64_modules(n, g, train):
         assert torch.allclose(mlps[1].running_mean.double(), ref[1].running_mean, atol=1e-5)
         assert torch.allclose(mlps[1].running_var.double(), ref[1].running_var, rtol=1e-5, atol=1e-6)
     assert int(mlps[1].num_batches_tracked) == int(ref[1].num_batches_tracked)
+
+
+@pytest.mark.parametrize("n,M,ns,cn,cf,mlp", [(5000, 700, 32, 10, 6, [32, 32, 64]), (3000, 500, 32, 10, 64, [64, 64, 128]),
+                                              (900, 37, 24, 10, 256, [256, 256, 512]), (4000, 1000, 16, 10, 0, [32, 64])])
+def test_gather_fused_first_layer_equals_materialised_rows(n, M, ns, cn, cf, mlp):
+    """First shared-MLP layer reading its rows through TMA gather4 from the per-point table (RSB_OPND_GATHER, forward and
+    weight gradient) and scattering the input gradient from the GEMM epilogue, against the same block fed with the row
+    matrix group_rows_fwd materialises: forward bit-identical (same subtraction, same GEMM), gradients to atomics' order."""
+    import copy
+    from repsurf_b200.mlp import gather_rows, group_rows, sa_mlp
+    g = torch.Generator().manual_seed(n + M)
+    xyz = torch.rand(n, 3, generator=g).to(cuda)
+    new_xyz = xyz[torch.randperm(n, generator=g)[:M].to(cuda)].contiguous()
+    idx = torch.randint(0, n, (M, ns), generator=g, dtype=torch.int32).to(cuda)
+    normal = torch.randn(n, cn, generator=g).to(cuda)
+    feat = torch.randn(n, cf, generator=g).to(cuda) if cf else None
+    blk = _Block(3, cn + cf, mlp, 1).to(cuda).train()
+    ref = copy.deepcopy(blk)
+    na, fa = normal.clone().requires_grad_(True), (feat.clone().requires_grad_(True) if cf else None)
+    nb, fb = normal.clone().requires_grad_(True), (feat.clone().requires_grad_(True) if cf else None)
+    out = sa_mlp(gather_rows(xyz, new_xyz, idx, na, fa, ns), 3, blk, ns)
+    rows, layout = group_rows(xyz, new_xyz, idx, nb, fb, ns, False)
+    want = sa_mlp(rows, 3, ref, ns, layout)
+    assert torch.equal(out, want)
+    go = torch.randn_like(out)
+    out.backward(go)
+    want.backward(go)
+    assert _rel(na.grad, nb.grad) < 1e-5
+    if cf:
+        assert _rel(fa.grad, fb.grad) < 1e-5
+    for (name, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        assert _rel(p.grad, q.grad) < 2e-5 or float(q.grad.abs().max()) == 0.0, name
+    for a, b in zip(blk.buffers(), ref.buffers()):
+        assert torch.equal(a, b)
