@@ -260,7 +260,8 @@ TIMED_ENTRIES = {"rsb_furthestsampling_packed", "rsb_furthestsampling_packed_bou
 
 
 def opnd_bytes(o, rows):
-    per_row = {0: o.K, 1: o.K, 2: 2 * o.K, 3: o.K + min(o.K, o.ku), 4: o.K}[o.kind]
+    # gathered operand (kind 5): the row index + the gathered table row (fused gather m*ns*(4 + 4C) bytes)
+    per_row = {0: o.K, 1: o.K, 2: 2 * o.K, 3: o.K + min(o.K, o.ku), 4: o.K, 5: o.K + 1}[o.kind]
     return rows * per_row * 4
 
 

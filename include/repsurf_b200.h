@@ -307,10 +307,10 @@ int rsb_pool_bn_backward_dense(long G, int ns, int C, const float *dm, const int
 /* rsb_bn_apply: out = [relu](sc*Y + sh) (materialised BatchNorm(+ReLU) output). */
 int rsb_bn_apply(long rows, int C, const float *Y, int ldy, const float *sc, const float *sh, int relu, float *out,
                  int ldo, cudaStream_t stream);
-/* rsb_bn_relu_backward: in place dA := dA where (sc*Y+sh [+ second half when dual]) > 0 else 0  (ReLU backward of
- *   a layer whose pre-BatchNorm output Y was stored), and stats[2C | 3C] += (sum dZ, sum dZ*xhat_1 [, sum dZ*xhat_2]). */
-int rsb_bn_relu_backward(long rows, int C, float *dA, int ldd, const float *Y, int ldy, const float *sc,
-                         const float *sh, const float *mu, const float *inv, int dual, double *stats,
+/* rsb_bn_relu_backward: dA := src where (sc*Y+sh [+ second half when dual]) > 0 else 0  (ReLU backward of a layer whose
+ *   pre-BatchNorm output Y was stored; src NULL = in place), and stats[2C | 3C] += (sum dZ, sum dZ*xhat_1 [, sum dZ*xhat_2]). */
+int rsb_bn_relu_backward(long rows, int C, const float *src, int lds, float *dA, int ldd, const float *Y, int ldy,
+                         const float *sc, const float *sh, const float *mu, const float *inv, int dual, double *stats,
                          cudaStream_t stream);
 int rsb_bn_backward_coef(int C, long rows, const double *stats, int dual, const float *sc, const float *mu,
                          const float *inv, float *a, float *b, float *d, float *dgamma, float *dbeta,

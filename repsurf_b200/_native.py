@@ -73,7 +73,7 @@ _SIGS = {
     "rsb_pool_forward": [_l, _i, _i, _p, _i, _p, _p, _p, _p],
     "rsb_pool_backward_stats": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "rsb_bn_backward_coef": [_i, _l, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
-    "rsb_bn_relu_backward": [_l, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p],
+    "rsb_bn_relu_backward": [_l, _i, _p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p],
     "rsb_bn_apply": [_l, _i, _p, _i, _p, _p, _i, _p, _i],
     "rsb_pool_bn_backward_dense": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p],
 }

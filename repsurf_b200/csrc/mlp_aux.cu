@@ -140,7 +140,7 @@ __global__ void bn_bwd_coef_kernel(int C, double rows, const double *__restrict_
 // dZ = dA where the layer's activation was positive (z = sc*Y + sh [+ second BatchNorm half] > 0), in place;
 // stats += (sum dZ, sum dZ*xhat_1 [, sum dZ*xhat_2]) per channel.  Thread = one channel quad, grid-stride over
 // rows: coalesced 16-byte accesses, register accumulation, one shared-memory reduction + fp64 atomics per block.
-__global__ void __launch_bounds__(256) bn_relu_bwd_kernel(long rows, int C, float *__restrict__ dA, int ldd,
+__global__ void __launch_bounds__(256) bn_relu_bwd_kernel(long rows, int C, const float *src, int lds, float *dA, int ldd,
                                                           const float *__restrict__ Y, int ldy,
                                                           const float *__restrict__ sc, const float *__restrict__ sh,
                                                           const float *__restrict__ mu, const float *__restrict__ inv,
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_kernel(long rows, int C, floa
     float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     const long r0 = (long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     for (long r = r0 + rlane; r < r1; r += rstep) {
-        float4 d = *reinterpret_cast<float4 *>(dA + (size_t)r * ldd + c);
+        float4 d = *reinterpret_cast<const float4 *>(src + (size_t)r * lds + c);    // src == dA: in place
         const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + (size_t)r * ldy + c));
         float4 y2 = make_float4(0, 0, 0, 0);
         float z[4] = {fmaf(y.x, a1.x, b1.x), fmaf(y.y, a1.y, b1.y), fmaf(y.z, a1.z, b1.z), fmaf(y.w, a1.w, b1.w)};
@@ -273,10 +273,12 @@ RSB_EXPORT int rsb_bn_apply(long rows, int C, const float *Y, int ldy, const flo
     return 0;
 }
 
-RSB_EXPORT int rsb_bn_relu_backward(long rows, int C, float *dA, int ldd, const float *Y, int ldy, const float *sc,
-                                    const float *sh, const float *mu, const float *inv, int dual, double *stats,
+RSB_EXPORT int rsb_bn_relu_backward(long rows, int C, const float *src, int lds, float *dA, int ldd, const float *Y, int ldy,
+                                    const float *sc, const float *sh, const float *mu, const float *inv, int dual, double *stats,
                                     cudaStream_t stream)
 {
+    if (!src) { src = dA; lds = ldd; }
+    RSB_REQUIRE(lds % 4 == 0 && ((uintptr_t)src % 16 == 0), "source gradient must be 16-byte aligned with a pitch multiple of 4");
     RSB_REQUIRE(C >= 4 && C % 4 == 0 && C <= 1024 && ldd % 4 == 0 && ldy % 4 == 0, "channels / pitches must be multiples of 4");
     RSB_REQUIRE(((uintptr_t)dA % 16 == 0) && ((uintptr_t)Y % 16 == 0), "tensors must be 16-byte aligned");
     if (rows == 0) return 0;
@@ -290,7 +292,7 @@ RSB_EXPORT int rsb_bn_relu_backward(long rows, int C, float *dA, int ldd, const 
     if (rpb < min_rpb) rpb = min_rpb;
     const int blocks = (int)((rows + rpb - 1) / rpb);
     RSB_REQUIRE(threads <= 256, "too many channels");
-    bn_relu_bwd_kernel<<<blocks, threads, 0, stream>>>(rows, C, dA, ldd, Y, ldy, sc, sh, mu, inv, dual, stats, (int)rpb);
+    bn_relu_bwd_kernel<<<blocks, threads, 0, stream>>>(rows, C, src, lds, dA, ldd, Y, ldy, sc, sh, mu, inv, dual, stats, (int)rpb);
     RSB_CHECK_LAUNCH("bn_relu_bwd_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;

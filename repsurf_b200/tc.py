@@ -386,13 +386,14 @@ class _LinearBN(Function):
         dev = X.device
         R, K = X.shape
         Nn = W2.shape[0]
-        dZ = dOut.contiguous().clone()
+        dOut = dOut.contiguous()
+        dZ = torch.empty_like(dOut)          # masked gradient written out of place (no clone of the incoming gradient)
         st = torch.zeros(2 * Nn, dtype=torch.float64, device=dev)
         if ctx.relu:
             msc, msh = sc, sh
         else:   # no activation: mask always on (z = 0*y + 1 > 0), statistics still needed
             msc, msh = torch.zeros(Nn, device=dev), torch.ones(Nn, device=dev)
-        N.call("rsb_bn_relu_backward", R, Nn, dZ, Nn, Y, Nn, msc, msh, mu, inv, 0, st)
+        N.call("rsb_bn_relu_backward", R, Nn, dOut, Nn, dZ, Nn, Y, Nn, msc, msh, mu, inv, 0, st)
         co = torch.empty(5, Nn, device=dev)
         N.call("rsb_bn_backward_coef", Nn, R, st, 2 if ctx.frozen else 0, sc, mu, inv, co[0], co[1], co[2], co[3], co[4])
         G = opnd(OPND_AFFINE2, dZ, Nn, a=co[0], b=co[1], d=co[2], V=Y, ku=Nn)

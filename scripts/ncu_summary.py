@@ -62,7 +62,7 @@ def main():
     # the longest launch otherwise
     fam = {}
     for d in allk:
-        name = "fps_kernel" if "fps_kernel" in d["kernel"] else "knn_grid_kernel" if "knn_grid" in d["kernel"] else \
+        name = "fps_kernel" if "fps" in d["kernel"] else "knn_grid_kernel" if "knn_grid" in d["kernel"] else \
             "gemm_wgrad_kernel" if "wgrad" in d["kernel"] else "gemm_rows_kernel" if "gemm_rows" in d["kernel"] else d["kernel"]
         gemm = name.startswith("gemm_")
         key = (lambda e: e["dram_bytes"]) if gemm else (lambda e: e["ms"])
