@@ -231,6 +231,28 @@ __device__ void knn_heap_replay_grid(const float *__restrict__ cand, int start, 
     __syncwarp();
 }
 
+// ---- k <= 32: the top-k list is ONE 64-bit key per lane, (distance bits << 32) | index: squared distances are non-negative
+// floats, so unsigned key order == lexicographic (distance, index) order.  A batch of 32 candidates that beats the current
+// k-th key is either inserted one by one (few survivors: ballot + popc rank, two shuffles) or, when many survive (the first
+// batches of every query), sorted by a 15-stage bitonic network and merged with the list in 6 more stages - a fixed ~170
+// instructions instead of ~40 per inserted candidate (ncu, profiles/r02_ncu_full_seg.md: the kernel is issue-bound, 66-73 %).
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src)
+{
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, int m)
+{
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, int d)
+{
+    const unsigned lo = __shfl_up_sync(0xffffffffu, (unsigned)v, d), hi = __shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), d);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long knn_key(float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; }
+
 template <int KPL, bool HEAP>
 __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
 {
@@ -257,6 +279,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
     int kth_i = sentinel_idx;
     bool tie = false;
     const int kth_lane = (k - 1) / KPL, kth_slot = (k - 1) % KPL;
+    unsigned long long L = knn_key(sentinel_d, sentinel_idx), kth_key = L;      // KPL == 1: this lane's list entry, the k-th key
 
     const int cx = cell_coord(qx, g.ox, g.inv_h, g.gx), cy = cell_coord(qy, g.oy, g.inv_h, g.gy), cz = cell_coord(qz, g.oz, g.inv_h, g.gz);
     const int *cs = P.cell_start + g.cell_base;
@@ -274,6 +297,63 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
                 const float4 p = __ldg(P.sorted + j);
                 d = rsb_sqdist(qx, qy, qz, p.x, p.y, p.z);
                 ci = __float_as_int(p.w) - index_base;
+            }
+            if constexpr (KPL == 1) {
+                unsigned long long ck = j < j1 ? knn_key(d, ci) : ~0ull;
+                // survivors: strictly better than the k-th key; HEAP semantics also needs to know about candidates that only
+                // TIE with the k-th distance (they decide between the list and the exact replay)
+                unsigned mask = __ballot_sync(0xffffffffu, ck < kth_key);
+                if (HEAP && __any_sync(0xffffffffu, j < j1 && d == kth_d)) tie = true;
+                const int ns = __popc(mask);
+                if (ns == 0) continue;
+                if (ns <= 4) {
+                    while (mask) {
+                        const int l = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const unsigned long long c = shfl64(ck, l);
+                        if (!(c < kth_key)) {                                           // the k-th key moved meanwhile
+                            if (HEAP && (unsigned)(c >> 32) == (unsigned)(kth_key >> 32)) tie = true;
+                            continue;
+                        }
+                        if (HEAP && __any_sync(0xffffffffu, (unsigned)(L >> 32) == (unsigned)(c >> 32))) tie = true;
+                        const int ins = __popc(__ballot_sync(0xffffffffu, L < c));      // list entries in front of it
+                        const unsigned long long up = shfl_up64(L, 1);
+                        L = lane > ins ? up : (lane == ins ? c : L);
+                        kth_key = shfl64(L, k - 1);
+                    }
+                } else {
+                    // bitonic sort of the batch (ascending), then merge: the 32 smallest of list + batch, sorted
+                    if (!(ck < kth_key)) ck = ~0ull;
+#pragma unroll
+                    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                        for (int jj = k2 >> 1; jj > 0; jj >>= 1) {
+                            const unsigned long long o = shfl_xor64(ck, jj);
+                            const bool take_min = ((lane & jj) == 0) == ((lane & k2) == 0 || k2 == 32);
+                            ck = take_min ? (ck < o ? ck : o) : (ck < o ? o : ck);
+                        }
+                    const unsigned long long rev = shfl64(ck, 31 - lane);                // descending batch
+                    unsigned long long m = L < rev ? L : rev;
+                    const unsigned long long dis = L < rev ? rev : L;                   // the 32 discarded keys
+#pragma unroll
+                    for (int jj = 16; jj > 0; jj >>= 1) {
+                        const unsigned long long o = shfl_xor64(m, jj);
+                        m = ((lane & jj) == 0) ? (m < o ? m : o) : (m < o ? o : m);
+                    }
+                    L = m;
+                    kth_key = shfl64(L, k - 1);
+                    if (HEAP) {
+                        // equal distances next to each other among the first k + 1 entries, or a discarded key that ties with the
+                        // new k-th distance: order / membership is decided by the heap's insertion history -> exact replay
+                        const unsigned kd = (unsigned)(kth_key >> 32);
+                        const unsigned prevd = __shfl_up_sync(0xffffffffu, (unsigned)(L >> 32), 1);
+                        const bool adj = lane > 0 && lane <= k && lane < 32 && prevd == (unsigned)(L >> 32) && (unsigned)(L >> 32) != __float_as_uint(sentinel_d);
+                        if (__any_sync(0xffffffffu, adj || (dis != ~0ull && (unsigned)(dis >> 32) == kd && kd != __float_as_uint(sentinel_d)))) tie = true;
+                    }
+                }
+                kth_d = __uint_as_float((unsigned)(kth_key >> 32));
+                kth_i = (int)(unsigned)kth_key;
+                continue;
             }
             unsigned mask = __ballot_sync(0xffffffffu, j < j1 && d <= kth_d);
             while (mask) {
@@ -363,6 +443,10 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
             if (od) od[i] = P.sqrt_out ? sqrtf(hd[i]) : hd[i];
         }
         return;
+    }
+    if constexpr (KPL == 1) {
+        ld[0] = __uint_as_float((unsigned)(L >> 32));
+        li[0] = (int)(unsigned)L;
     }
 #pragma unroll
     for (int t = 0; t < KPL; t++) {
