@@ -286,15 +286,36 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
     const int rmax = max(max(g.gx, g.gy), g.gz);
 
     unsigned n_cand = 0, n_ranges = 0;
-    auto scan_range = [&](int j0, int j1) {
-        n_cand += (unsigned)max(j1 - j0, 0);
-        n_ranges++;
-        for (int base = j0; base < j1; base += 32) {
-            const int j = base + lane;
+    // One call scans up to 32 cell ranges, lane t holding range t = [my_s, my_e) of the cell-sorted point array: the ranges are
+    // concatenated virtually and walked in full 32-candidate batches (a 27-cell neighbourhood is ~10 ranges of ~20 points: one
+    // batch PER RANGE left a third of the lanes idle and chained two dependent global loads per range)
+    auto scan_ranges = [&](int my_s, int my_e) {
+        const int len = max(my_e - my_s, 0);
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        n_cand += (unsigned)total;
+        n_ranges += (unsigned)__popc(__ballot_sync(0xffffffffu, len > 0));
+        for (int base = 0; base < total; base += 32) {
+            const int pos = base + lane;
+            const int j1 = 1, j = pos < total ? 0 : 1;            // "j < j1"  <=>  this lane holds a candidate
+            // range of this position: first lane whose inclusive prefix exceeds it (binary search over the warp's prefixes)
+            int slot = 0;
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, slot + st - 1);
+                if (v <= pos) slot += st;
+            }
+            slot = min(slot, 31);
+            const int rs = __shfl_sync(0xffffffffu, my_s, slot), rexcl = __shfl_sync(0xffffffffu, incl - len, slot);
             float d = CUDART_INF_F;
             int ci = 0;
             if (j < j1) {
-                const float4 p = __ldg(P.sorted + j);
+                const float4 p = __ldg(P.sorted + rs + (pos - rexcl));
                 d = rsb_sqdist(qx, qy, qz, p.x, p.y, p.z);
                 ci = __float_as_int(p.w) - index_base;
             }
@@ -401,17 +422,27 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
         const int z0 = max(cz - r, 0), z1 = min(cz + r, g.gz - 1);
         const int y0 = max(cy - r, 0), y1 = min(cy + r, g.gy - 1);
         const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
-        for (int z = z0; z <= z1; z++)
-            for (int y = y0; y <= y1; y++) {
+        // every (z, y) row of the ring contributes two range slots: a shell row its whole x span (+ an empty slot), an inner
+        // row its left and its right boundary cell; 32 slots per pass, each lane fetching the two cell starts of its own slot
+        const int ny = y1 - y0 + 1, n_slots = 2 * (z1 - z0 + 1) * ny;
+        for (int t0 = 0; t0 < n_slots; t0 += 32) {
+            const int t = t0 + lane;
+            int my_s = 0, my_e = 0;
+            if (t < n_slots) {
+                const int row = t >> 1, which = t & 1;
+                const int z = z0 + row / ny, y = y0 + row % ny;
                 const int rowbase = (z * g.gy + y) * g.gx;
                 const bool shell_row = (abs(z - cz) == r) || (abs(y - cy) == r);
                 if (shell_row) {
-                    scan_range(cs[rowbase + x0], cs[rowbase + x1 + 1]);
-                } else {
-                    if (cx - r >= 0) scan_range(cs[rowbase + cx - r], cs[rowbase + cx - r + 1]);
-                    if (cx + r < g.gx && r > 0) scan_range(cs[rowbase + cx + r], cs[rowbase + cx + r + 1]);
+                    if (which == 0) { my_s = __ldg(cs + rowbase + x0); my_e = __ldg(cs + rowbase + x1 + 1); }
+                } else if (which == 0) {
+                    if (cx - r >= 0) { my_s = __ldg(cs + rowbase + cx - r); my_e = __ldg(cs + rowbase + cx - r + 1); }
+                } else if (cx + r < g.gx && r > 0) {
+                    my_s = __ldg(cs + rowbase + cx + r); my_e = __ldg(cs + rowbase + cx + r + 1);
                 }
             }
+            scan_ranges(my_s, my_e);
+        }
         // conservative termination: distance to the nearest face of the explored cube that still has cells behind it
         float face = CUDART_INF_F;
         if (cx - r > 0) face = fminf(face, qx - (g.ox + (float)(cx - r) * g.h));

@@ -44,6 +44,9 @@ def strided_offsets(offset, stride):
 _ACTIVE_PLAN = None
 # first shared-MLP layer reads its rows through a TMA gather instead of a materialised row matrix (levels without polar columns)
 FUSE_GATHER = True
+# GeometryPlan runs sampling / neighbour search on side streams; False = everything in order on the caller's stream (per-kernel
+# timing without interference from concurrent kernels: bench.py's roofline pass)
+USE_SIDE_STREAMS = True
 _SIDE_STREAMS = {}
 
 
@@ -71,7 +74,7 @@ class GeometryPlan:
     def __init__(self, center, offset, levels, training, fp_k=3):
         dev = center.device
         main = torch.cuda.current_stream(dev)
-        s_fps, s_knn = _side_streams(dev)
+        s_fps, s_knn = _side_streams(dev) if USE_SIDE_STREAMS else (main, main)
         start = torch.cuda.Event()
         start.record(main)
         self.sa, self.knn = {}, {}
