@@ -338,14 +338,21 @@ __global__ void __launch_bounds__(RowsCfg<XFW, ES>::THREADS, 1) gemm_rows2_kerne
                 bulk_g2s(w_res, P.Wp, w_res_bytes, &B->w_bar);
             }
             uint32_t it = 0;
+            int idn[4];       // neighbour indices of the NEXT work item's rows (loaded one item ahead: no load latency in the loop)
+#pragma unroll
+            for (int e = 0; e < 4; e++) idn[e] = __ldg(A.arg + min(((long)blockIdx.x / per_tile) * TM + 4 * lane + e, P.rows - 1));
             for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
                 const long tile = w / per_tile;
                 const int rem = (int)(w - tile * per_tile);
                 const int nt = rem / NS, sub = rem - nt * NS;
-                const long r0 = tile * TM + 4 * lane;
                 int id[4];
 #pragma unroll
-                for (int e = 0; e < 4; e++) id[e] = __ldg(A.arg + min(r0 + e, P.rows - 1));
+                for (int e = 0; e < 4; e++) id[e] = idn[e];
+                if (w + gridDim.x < n_work) {
+                    const long r1 = ((w + gridDim.x) / per_tile) * TM + 4 * lane;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) idn[e] = __ldg(A.arg + min(r1 + e, P.rows - 1));
+                }
                 for (int kc = 0; kc < KCH; kc++, it++) {
                     const int s = it % S;
                     mbar_wait(&B->empty[s], ((it / S) & 1) ^ 1);
@@ -448,6 +455,25 @@ __global__ void __launch_bounds__(RowsCfg<XFW, ES>::THREADS, 1) gemm_rows2_kerne
             const int col0 = nt * NT + sub * NTs;              // first output column of this work item
             const long row = tile * TM + q * 32 + lane;
             const bool row_ok = row < P.rows;
+            if (mask) {
+                // the mask operand of this warp set's NEXT work item starts its way from DRAM to L2 now: the epilogue reads it
+                // row by row with plain loads, a latency chain that would otherwise start only after the accumulator is ready
+                const long wn = w + (long)gridDim.x * ES;
+                if (wn < n_work) {
+                    const long tn = wn / per_tile;
+                    const int remn = (int)(wn - tn * per_tile);
+                    const int ntn = remn / NS, subn = remn - ntn * NS;
+                    const long rn = tn * TM + q * 32 + lane;
+                    if (rn < P.rows) {
+                        const float *yn = E.Yl + (size_t)rn * E.ldl + ntn * NT + subn * NTs;
+                        const int ncn = min(NTs, P.N - (ntn * NT + subn * NTs));
+                        for (int c0 = 0; c0 < ncn; c0 += 32) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(yn + c0));
+                            if (E.dual) asm volatile("prefetch.global.L2 [%0];" ::"l"(yn + P.N + c0));
+                        }
+                    }
+                }
+            }
             mbar_wait(&B->acc_full[ab], (acc_it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
@@ -737,15 +763,22 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
                 // chunk for box l / 8, then lanes + 32 ... until all xb boxes are issued
                 const uint32_t tx = (uint32_t)(P.g_pieces * gb + xb) * BOX;
                 uint32_t it = 0;
+                const int g4 = lane & 7;
+                int idn[4];   // neighbour indices of the next chunk's rows, loaded one chunk ahead
+#pragma unroll
+                for (int e = 0; e < 4; e++) idn[e] = __ldg(P.X.arg + min(c_begin * KC + 4 * g4 + e, P.rows - 1));
                 for (long ci = 0; ci < my_chunks; ci++, it++) {
                     const int s = it % S;
+                    int id[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) id[e] = idn[e];
+                    if (ci + 1 < my_chunks) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) idn[e] = __ldg(P.X.arg + min((c_begin + ci + 1) * KC + 4 * g4 + e, P.rows - 1));
+                    }
                     mbar_wait(&B->empty[s], ((it / S) & 1) ^ 1);
                     const uint32_t st = base + (uint32_t)s * stage_bytes;
                     const int row0 = (int)((c_begin + ci) * KC);
-                    const int g4 = lane & 7;
-                    int id[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) id[e] = __ldg(P.X.arg + min((long)row0 + 4 * g4 + e, P.rows - 1));
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&B->raw_full[s], tx);
                         for (int g = 0; g < gb; g++) {
