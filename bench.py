@@ -485,9 +485,17 @@ def build_rooflines(per_entry, knn_work, ms_step, steps, workload):
     fam = {"rsb_gemm_wgrad": ("gemm_wgrad2_kernel", "gemm_wgrad_kernel"), "rsb_gemm_rows": ("gemm_rows2_kernel", "gemm_rows_kernel"),
            "rsb_knnquery_grid": ("knn_grid_kernel",), "rsb_furthestsampling_packed": ("fps2_kernel", "fps_kernel"),
            "rsb_furthestsampling_packed_bounded": ("fps2_kernel", "fps_kernel"), "rsb_furthestsampling_dense": ("fps2_kernel", "fps_kernel")}
+    shape_traffic = {}
+    sp = os.path.join(ROOT, "profiles", "r02_ncu_gemm_traffic.json")
+    if os.path.exists(sp):
+        shape_traffic = json.load(open(sp))["by_shape"]
     for name, r in rooflines.items():
-        t = next((traffic[f] for f in fam.get(name, ()) if f in traffic), None)
-        r["traffic"] = t["dram_bytes"] if t else None
+        if name.startswith("rsb_gemm") or name.startswith("gemm_"):
+            # GEMM launches run at many shapes: DRAM traffic only where the ncu capture holds the SAME launch shape
+            r["traffic"] = next((v for k, v in shape_traffic.items() if r["launch"].startswith(k)), None)
+        else:
+            t = next((traffic[f] for f in fam.get(name, ()) if f in traffic), None)
+            r["traffic"] = t["dram_bytes"] if t else None
         r["peak_source"] = peak_src
     return rooflines, entry_share
 
