@@ -35,17 +35,31 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_flat_gradient_allreduce_matches_single_process():
+def _run_two_ranks():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    try:
+        res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    except Exception:
+        res = None
     for p in procs:
         p.join(timeout=60)
-        assert p.exitcode == 0
+        if p.is_alive():
+            p.kill()
+    if res is None or any(p.exitcode != 0 for p in procs):
+        return None
+    return res
+
+
+def test_two_rank_flat_gradient_allreduce_matches_single_process():
+    # the rendezvous port is picked free and then bound by the workers: another process can take it in between (seen once on
+    # a loaded box) - a second attempt with a fresh port is allowed, the numerical assertions below are not retried
+    res = _run_two_ranks() or _run_two_ranks()
+    assert res is not None, "two-rank gloo run failed twice"
     (_, g0, w0), (_, g1, w1) = res
     assert torch.equal(w0, w1)                          # broadcast made the replicas identical
     assert torch.allclose(g0, g1, rtol=0, atol=0)       # every rank holds the same averaged gradient
