@@ -291,7 +291,11 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
     torch.manual_seed(rank)
     np.random.seed(rank)
     model = (RepSurfSeg() if workload == "seg" else RepSurfCls()).to(dev).train()
-    crit = nn.CrossEntropyLoss() if workload == "seg" else SmoothClsLoss()
+    if workload == "seg":
+        from repsurf_b200.seg.loss import CrossEntropyLoss      # the step's criterion (nn.CrossEntropyLoss semantics), one kernel
+        crit = CrossEntropyLoss()
+    else:
+        crit = SmoothClsLoss()
     params = [p for p in model.parameters()]
     broadcast_module(model)
     # gradients are packed into one flat buffer after backward: ONE all-reduce per step (3.9 MB seg / 5.9 MB cls)

@@ -325,6 +325,13 @@ int rsb_scene_vote(long rows, int num_class, const float *logits, int ld, const 
 int rsb_scene_decide(long n, int num_class, const float *pred, const float *count, int *label, cudaStream_t stream);
 int rsb_label_median(long n, int k, const int *nbr, const int *label, int *out, cudaStream_t stream);
 
+/* Cross-entropy of the segmentation step (segmentation/tool/train.py: nn.CrossEntropyLoss(ignore_index)), one pass:
+ * loss = mean over rows with target != ignore_index of (logsumexp(x) - x[target]); grad = softmax(x) - onehot(target) is written
+ * by the forward (unscaled, zero on ignored rows) and scaled by upstream / #valid rows in the backward.  acc: fp64[2], pre-zeroed. */
+int rsb_cross_entropy_forward(long rows, int num_class, const float *logits, int ld, const long long *target,
+                              long long ignore_index, float *grad, int ldg, double *acc, float *loss, cudaStream_t stream);
+int rsb_cross_entropy_backward(long n_elements, float *grad, const double *acc, const float *upstream, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ classification evaluation harness
  * replaces the torch-native FPS resampling of sample()            classification/modules/pointnet2_utils.py:62-75, :114-124
  * feat [b,c,n] channel-first (xyz = channels 0..2), start [b] int64 first picks; idx [b,m] int64, out [b,c,m] = feat[:, :, idx].

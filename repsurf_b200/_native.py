@@ -49,6 +49,8 @@ _SIGS = {
     "rsb_voxel_pick": [_i, _p, _p, _p, _p, _p],
     "rsb_seed_distance": [_l, _p, _l, _p],
     "rsb_point_table": [_l, _i, _i, _i, _p, _p, _p, _p],
+    "rsb_cross_entropy_forward": [_l, _i, _p, _i, _p, ctypes.c_longlong, _p, _i, _p, _p],
+    "rsb_cross_entropy_backward": [_l, _p, _p, _p],
     "rsb_sector_split": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p],
     "rsb_sector_map_back": [_i, _p, _p, _p],
     "rsb_knnquery_packed": [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i],

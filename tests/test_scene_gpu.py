@@ -117,3 +117,26 @@ def test_scene_inference_loop_runs_eval_model_on_crops():
     # a second pass reproduces the labels (eval mode: no batch statistics, no dropout; the umbrella flip is seeded)
     np.random.seed(0)
     assert torch.equal(S.scene_inference(model, coords, feats, crops, n, 13, batch_size=2, filter_k=32, coord_all=xyz), lab)
+
+
+@pytest.mark.parametrize("rows,nc,ignore", [(50_000, 13, None), (4097, 13, 255), (1000, 20, 3)])
+def test_cross_entropy_matches_torch(rows, nc, ignore):
+    """seg/loss.CrossEntropyLoss (one kernel: value + gradient) against nn.CrossEntropyLoss in fp64, on the row-padded logits
+    view the classifier head produces, with ignored rows."""
+    import torch.nn as nn
+    from repsurf_b200.seg.loss import CrossEntropyLoss
+    g = torch.Generator().manual_seed(rows)
+    buf = (torch.randn(rows, (nc + 3) // 4 * 4, generator=g) * 3).to(cuda)
+    target = torch.randint(0, nc, (rows,), generator=g).to(cuda)
+    if ignore is not None:
+        target[torch.rand(rows, generator=g).to(cuda) < 0.2] = ignore
+    a = buf.clone().requires_grad_(True)
+    b = buf[:, :nc].double().detach().requires_grad_(True)
+    kw = {} if ignore is None else {"ignore_index": ignore}
+    la = CrossEntropyLoss(**kw)(a[:, :nc], target)
+    lb = nn.CrossEntropyLoss(**kw)(b, target)
+    assert abs(float(la) - float(lb)) < 1e-5 * max(1.0, abs(float(lb)))
+    (la * 1.7).backward()
+    (lb * 1.7).backward()
+    assert float(a.grad[:, nc:].abs().sum()) == 0.0
+    assert float((a.grad[:, :nc].double() - b.grad).abs().max()) < 1e-6 * float(b.grad.abs().max()) + 1e-12
