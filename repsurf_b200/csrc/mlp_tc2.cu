@@ -51,7 +51,8 @@ struct RowsCfg {
     static constexpr int XF_W = XFW, XF_T = XFW * 32, LOAD_W = XFW, MMA_W = XFW + 1, EPI_W0 = XFW + 2, EPI_N = 4 * ES,
                          THREADS = (XFW + 2 + 4 * ES) * 32, PIECES = (TM * KC * 4 / 16) / (XFW * 32);
 };
-constexpr int STAGES_MAX = 4;
+constexpr int STAGES_MAX = 4;           // gemm_rows2
+constexpr int W_STAGES_MAX = 10;        // gemm_wgrad2 (small stages: depth hides the TMA latency)
 constexpr int SMEM_MAX = 227 * 1024;
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------------
@@ -151,7 +152,7 @@ __device__ __forceinline__ float4 xform(int kind, const float4 u, const float4 w
 }
 
 struct alignas(16) Bars2 {
-    uint64_t raw_full[STAGES_MAX], full[STAGES_MAX], empty[STAGES_MAX], acc_full[2], acc_empty[2], w_bar;
+    uint64_t raw_full[W_STAGES_MAX], full[W_STAGES_MAX], empty[W_STAGES_MAX], acc_full[2], acc_empty[2], w_bar;
     uint32_t tmem_slot, pad;
 };
 
@@ -159,7 +160,7 @@ template <int COLS>
 __device__ __forceinline__ uint32_t cta_setup(Bars2 *B, int tid, int warp, int full_count, int mma_warp = MMA_WARP)
 {
     if (tid == 0) {
-        for (int s = 0; s < STAGES_MAX; s++) { mbar_init(&B->raw_full[s], 1); mbar_init(&B->full[s], full_count); mbar_init(&B->empty[s], 1); }
+        for (int s = 0; s < W_STAGES_MAX; s++) { mbar_init(&B->raw_full[s], 1); mbar_init(&B->full[s], full_count); mbar_init(&B->empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&B->acc_full[a], 1); mbar_init(&B->acc_empty[a], 128); }
         mbar_init(&B->w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -632,6 +633,7 @@ struct Wgrad2Params {
     long rows;
     int M, N, NT, NTB, m_tiles, n_tiles, splits, stages;
     int g_pieces, x_pieces;
+    int GB;           // 32-channel boxes per G part of a stage (ceil(min(M, 128) / 32))
     int x_gather;     // X rows are gathered by index (TMA gather4) and centred (RSB_OPND_GATHER)
 };
 
@@ -648,7 +650,13 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
 
     const int NT = P.NT, NTB = P.NTB, S = P.stages;
     const uint32_t x_bytes = (uint32_t)NTB * BOX;                   // one of raw/hi, raw/lo of the X tile
-    const uint32_t stage_bytes = 2 * A_TILE + 2 * x_bytes;
+    // stage = [G hi/raw0 | G lo/raw1 | X hi/raw0 | X lo/raw1], each G part only as many 32-channel boxes as the matrix has (GB <= 4):
+    // the sa1 launches have 32 or 64 gradient channels, and with a full 128-channel slot per part three quarters of a stage were
+    // padding - the freed shared memory becomes pipeline depth (the kernel is latency-bound on its TMA loads: ncu long-scoreboard
+    // stall 4-7 per issue at 20-36 % DRAM, profiles/r02_ncu_full_seg.md).  The MMA still reads 4 boxes per part; the ones beyond GB
+    // alias the following parts and only feed accumulator rows nobody reads.
+    const uint32_t g_bytes = (uint32_t)P.GB * BOX;
+    const uint32_t stage_bytes = 2 * g_bytes + 2 * x_bytes;
     constexpr int TABW = TM + 256;
     float *ctab = reinterpret_cast<float *>(gbase + (size_t)S * stage_bytes);   // [a | b | d | a2 | d2] x (G 128 | X 256)
     Bars2 *B = reinterpret_cast<Bars2 *>(ctab + 5 * TABW);
@@ -721,17 +729,17 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
                     c.a2 = *reinterpret_cast<const float4 *>(ctab + 3 * TABW + ch);
                     c.d2 = *reinterpret_cast<const float4 *>(ctab + 4 * TABW + ch);
                     const float4 u = lds128(addr);
-                    const float4 x = g2 ? lds128(addr + A_TILE) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 x = g2 ? lds128(addr + g_bytes) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 v = xform(P.G.kind, u, x, c);
                     if (!row_ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 hi, lo;
                     split4(v, hi, lo);
                     sts128(addr, hi);
-                    sts128(addr + A_TILE, lo);
+                    sts128(addr + g_bytes, lo);
                 }
                 // ---- X tile ----
                 for (int bx = box0; bx < xb; bx += 2) {
-                    const uint32_t addr = st + 2 * A_TILE + (uint32_t)(bx * 256 + (tid & 255)) * 16;
+                    const uint32_t addr = st + 2 * g_bytes + (uint32_t)(bx * 256 + (tid & 255)) * 16;
                     const int ch = TM + bx * 32 + q * 4;
                     Coef c;
                     c.a = *reinterpret_cast<const float4 *>(ctab + ch);
@@ -784,12 +792,12 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
                         for (int g = 0; g < gb; g++) {
                             const int c = mt * TM + g * 32;
                             tma_load_2d(st + (uint32_t)g * BOX, &P.mapG0, piece0_col(P.G, c), row0, &B->raw_full[s]);
-                            if (P.g_pieces == 2) tma_load_2d(st + A_TILE + (uint32_t)g * BOX, &P.mapG1, P.G.k0 + c, row0, &B->raw_full[s]);
+                            if (P.g_pieces == 2) tma_load_2d(st + g_bytes + (uint32_t)g * BOX, &P.mapG1, P.G.k0 + c, row0, &B->raw_full[s]);
                         }
                     }
                     __syncwarp();
                     for (int x = lane >> 3; x < xb; x += 4)
-                        tma_gather4(st + 2 * A_TILE + (uint32_t)x * BOX + (uint32_t)g4 * 512u, &P.mapX0, nt * NT + x * 32, id[0], id[1], id[2], id[3],
+                        tma_gather4(st + 2 * g_bytes + (uint32_t)x * BOX + (uint32_t)g4 * 512u, &P.mapX0, nt * NT + x * 32, id[0], id[1], id[2], id[3],
                                     &B->raw_full[s]);
                 }
             } else if (lane == 0) {
@@ -804,12 +812,12 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
                     for (int g = 0; g < gb; g++) {
                         const int c = mt * TM + g * 32;
                         tma_load_2d(st + (uint32_t)g * BOX, &P.mapG0, piece0_col(P.G, c), row0, &B->raw_full[s]);
-                        if (P.g_pieces == 2) tma_load_2d(st + A_TILE + (uint32_t)g * BOX, &P.mapG1, P.G.k0 + c, row0, &B->raw_full[s]);
+                        if (P.g_pieces == 2) tma_load_2d(st + g_bytes + (uint32_t)g * BOX, &P.mapG1, P.G.k0 + c, row0, &B->raw_full[s]);
                     }
                     for (int x = 0; x < xb; x++) {
                         const int c = nt * NT + x * 32;
-                        tma_load_2d(st + 2 * A_TILE + (uint32_t)x * BOX, &P.mapX0, piece0_col(P.X, c), row0, &B->raw_full[s]);
-                        if (P.x_pieces == 2) tma_load_2d(st + 2 * A_TILE + x_bytes + (uint32_t)x * BOX, &P.mapX1, P.X.k0 + c, row0, &B->raw_full[s]);
+                        tma_load_2d(st + 2 * g_bytes + (uint32_t)x * BOX, &P.mapX0, piece0_col(P.X, c), row0, &B->raw_full[s]);
+                        if (P.x_pieces == 2) tma_load_2d(st + 2 * g_bytes + x_bytes + (uint32_t)x * BOX, &P.mapX1, P.X.k0 + c, row0, &B->raw_full[s]);
                     }
                 }
             }
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t st = base + (uint32_t)s * stage_bytes;
-                    const uint32_t a_hi = st, a_lo = st + A_TILE, b_hi = st + 2 * A_TILE, b_lo = b_hi + x_bytes;
+                    const uint32_t a_hi = st, a_lo = st + g_bytes, b_hi = st + 2 * g_bytes, b_lo = b_hi + x_bytes;
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ks++) {
                         // MN-major, 32-byte swizzle atoms: 32-channel groups BOX bytes apart (LBO), 4-row groups 512 B apart
@@ -1010,10 +1018,12 @@ int rsb_gemm_wgrad2_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, 
     P.NTB = (P.NT + 31) / 32;
     P.g_pieces = (G->kind == RSB_OPND_DUAL_BN_RELU || G->kind == RSB_OPND_AFFINE2) ? 2 : 1;
     P.x_pieces = (X->kind == RSB_OPND_DUAL_BN_RELU || X->kind == RSB_OPND_AFFINE2) ? 2 : 1;
-    const size_t stage_b = 2 * (size_t)A_TILE + 2 * (size_t)P.NTB * BOX;
-    const size_t fixed = 5 * (size_t)(TM + 256) * 4 + sizeof(Bars2) + 1024 + 64;
+    P.GB = ((P.M < TM ? P.M : TM) + 31) / 32;
+    const size_t stage_b = 2 * (size_t)P.GB * BOX + 2 * (size_t)P.NTB * BOX;
+    // + 16 KB of slack behind the last stage: the MMA's 4-box read of the last G part may run past it (see the kernel)
+    const size_t fixed = 5 * (size_t)(TM + 256) * 4 + sizeof(Bars2) + 1024 + 64 + 4 * (size_t)BOX;
     int st = (int)((SMEM_MAX - fixed) / stage_b);
-    if (st > STAGES_MAX) st = STAGES_MAX;
+    if (st > W_STAGES_MAX) st = W_STAGES_MAX;
     if (st < 2) return -1;
     P.stages = st;
     const size_t smem = (size_t)st * stage_b + fixed;

@@ -155,7 +155,10 @@ def _sample_and_group(stride, nsample, center, normal, feature, offset, return_p
         else:
             fps_idx, new_center, new_offset = None, center, offset
         group_idx, _ = P.knnquery(nsample, center, new_center, offset, new_offset)
-    new_normal = normal[fps_idx, :] if fps_idx is not None else normal
+    # rows of `normal` at the sampled points: the packed grouping kernel with one sample per row (its backward scatters with
+    # atomics; torch's advanced indexing would sort the indices in its backward)
+    new_normal = P.grouping(normal.contiguous(), fps_idx.to(torch.int32).view(-1, 1)).view(fps_idx.shape[0], -1) \
+        if fps_idx is not None else normal
     if not return_polar and FUSE_GATHER:
         # the row matrix is never built: the first GEMMs gather [xyz | normal | feature] rows of a per-point table with TMA
         rows = gather_rows(center, new_center, group_idx, normal, feature, nsample)
