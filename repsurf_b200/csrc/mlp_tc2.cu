@@ -53,6 +53,8 @@ struct RowsCfg {
 };
 constexpr int STAGES_MAX = 4;           // gemm_rows2
 constexpr int W_STAGES_MAX = 10;        // gemm_wgrad2 (small stages: depth hides the TMA latency)
+constexpr int W_GROUPS = 2;             // gemm_wgrad2: transform warp groups, each owning every W_GROUPS-th chunk
+constexpr int W_GT = XF_THREADS / W_GROUPS;    // threads of a group: 256 = the 16-byte pieces of one 32 x 32 box
 constexpr int SMEM_MAX = 227 * 1024;
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------------
@@ -697,30 +699,31 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
         if (P.g_pieces == 2) prefetch_tmap(&P.mapG1);
         if (P.x_pieces == 2) prefetch_tmap(&P.mapX1);
     }
-    const uint32_t tmem_base = cta_setup<256>(B, tid, warp, XF_THREADS);
+    const uint32_t tmem_base = cta_setup<256>(B, tid, warp, W_GT);
 
     if (my_chunks > 0) {
         if (warp < XF_WARPS) {
             // =============================== transform warps ===============================
             // 16-byte piece p of a region: box p >> 8, k-row (p >> 3) & 31, physical chunk p & 7; with 32-byte swizzle atoms
-            // the logical channel quad is chunk ^ ((row & 3) << 1).  A thread's pieces tid + 512 j share row and quad.
-            const int kr = (tid >> 3) & 31;
-            const int q = (tid & 7) ^ ((kr & 3) << 1);
-            const int box0 = tid >> 8;                                   // boxes box0, box0 + 2, ...
+            // the logical channel quad is chunk ^ ((row & 3) << 1).
+            // The 16 warps work as W_GROUPS independent groups, group g owning the chunks ci = g (mod W_GROUPS): a thread's
+            // chunk is a ~1500-cycle dependent chain (mbarrier wait -> LDS -> transform -> STS -> proxy fence -> arrive), and with
+            // every thread walking EVERY chunk only one chunk per SM was in transformation at a time (0.8 us per 32-row chunk
+            // whatever the pipeline depth); now W_GROUPS chunks are.
+            const int grp = tid / W_GT, gtid = tid - grp * W_GT;
+            const int kr = (gtid >> 3) & 31;
+            const int q = (gtid & 7) ^ ((kr & 3) << 1);
             const bool g2 = P.g_pieces == 2, x2 = P.x_pieces == 2;
-            uint32_t it = 0;
-            for (long ci = 0; ci < my_chunks; ci++, it++) {
+            for (long ci = grp; ci < my_chunks; ci += W_GROUPS) {
+                const uint32_t it = (uint32_t)ci;
                 const int s = it % S;
                 const int lim = (int)min((long)KC, P.rows - (c_begin + ci) * KC);   // valid rows of this chunk
                 const bool row_ok = kr < lim;
                 mbar_wait(&B->raw_full[s], (it / S) & 1);
                 const uint32_t st = base + (uint32_t)s * stage_bytes;
-                // ---- G tile ----
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const int bx = box0 + 2 * j;
-                    if (bx >= gb) break;
-                    const uint32_t addr = st + (uint32_t)(tid + XF_THREADS * j) * 16;
+                // ---- G tile: boxes 0 .. gb - 1, one 16-byte piece per thread and box (W_GT == 256 pieces == one box) ----
+                for (int bx = 0; bx < gb; bx++) {
+                    const uint32_t addr = st + (uint32_t)(bx * 256 + gtid) * 16;
                     const int ch = bx * 32 + q * 4;
                     Coef c;
                     c.a = *reinterpret_cast<const float4 *>(ctab + ch);
@@ -738,8 +741,8 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
                     sts128(addr + g_bytes, lo);
                 }
                 // ---- X tile ----
-                for (int bx = box0; bx < xb; bx += 2) {
-                    const uint32_t addr = st + 2 * g_bytes + (uint32_t)(bx * 256 + (tid & 255)) * 16;
+                for (int bx = 0; bx < xb; bx++) {
+                    const uint32_t addr = st + 2 * g_bytes + (uint32_t)(bx * 256 + gtid) * 16;
                     const int ch = TM + bx * 32 + q * 4;
                     Coef c;
                     c.a = *reinterpret_cast<const float4 *>(ctab + ch);
