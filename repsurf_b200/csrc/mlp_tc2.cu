@@ -882,6 +882,183 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
     cta_teardown<256>(tmem_base, warp);
 }
 
+// ============================================================================================================
+// dW for NARROW layers (M <= 64 gradient channels, N <= 64 input channels) on the fp32 pipe
+// ============================================================================================================
+// The sa1 weight gradients are [32..64] x [20..64] matrices reduced over 2.6 M rows: 1-2 kFLOP per 250-500 bytes of operands.
+// On the tensor core the gradient tile is padded to UMMA's M = 128: three quarters of every operand read from shared memory
+// feed accumulator rows nobody uses, and with the in-place transform's own traffic the kernel sits at 55-75 % of the SM's
+// shared-memory bandwidth (ncu l1tex throughput; profiles/r02_ncu_full_seg.md) at 0.27-0.46 of the HBM roofline, whatever the
+// pipeline depth or the number of transform groups.  Here a warp streams 4 rows per 512-byte load (lane = row x channel quad),
+// applies the operand transform in registers, and every lane owns a (4 MQ) x (8 NO) block of dW in registers: per row
+// 4 MQ + 8 NO shuffles and 32 MQ NO FMAs.  Plain fp32 (no 3xTF32 split needed), HBM-bound.
+struct NarrowParams {
+    Opnd G, X;
+    float *dW;
+    int ldw;
+    long rows;
+    int M, N;
+};
+
+// raw 16-byte piece(s) of operand O at row r (already clamped), channel c (multiple of 4, < O.K)
+__device__ __forceinline__ void narrow_load(const Opnd &O, long r, int c, float4 &u, float4 &w)
+{
+    w = make_float4(0.f, 0.f, 0.f, 0.f);
+    switch (O.kind) {
+    case RSB_OPND_DUAL_BN_RELU:
+        u = __ldg(reinterpret_cast<const float4 *>(O.U + (size_t)r * O.ldu + O.k0 + c));
+        w = __ldg(reinterpret_cast<const float4 *>(O.U + (size_t)r * O.ldu + O.ku + O.k0 + c));
+        break;
+    case RSB_OPND_AFFINE2:
+        u = __ldg(reinterpret_cast<const float4 *>(O.U + (size_t)r * O.ldu + (O.k0 + c) % O.ku));
+        w = __ldg(reinterpret_cast<const float4 *>(O.V + (size_t)r * O.ldv + O.k0 + c));
+        break;
+    case RSB_OPND_GATHER: {
+        u = __ldg(reinterpret_cast<const float4 *>(O.U + (size_t)__ldg(O.arg + r) * O.ldu + c));
+        if (c == 0) {      // neighbour coordinates -> relative to the group centre
+            const float *cen = O.V + (r / O.ns) * 3;
+            u.x = __fsub_rn(u.x, __ldg(cen)); u.y = __fsub_rn(u.y, __ldg(cen + 1)); u.z = __fsub_rn(u.z, __ldg(cen + 2));
+        }
+        break;
+    }
+    default:
+        u = __ldg(reinterpret_cast<const float4 *>(O.U + (size_t)r * O.ldu + O.k0 + c));
+        break;
+    }
+}
+
+template <int MQ, int NO>
+__global__ void __launch_bounds__(256, (MQ * NO == 1) ? 3 : (MQ * NO == 2 ? 2 : 1)) wgrad_narrow_kernel(const NarrowParams P)
+{
+    __shared__ __align__(16) float4 s_coef[(MQ + NO) * 8][5];       // [operand quad][a, d, b, a2, d2]
+    __shared__ float s_dw[MQ * 32 * NO * 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int li = lane >> 3, lj = lane & 7;                          // load mapping: row li of the 4-row group, channel quad lj
+    for (int e = tid; e < (MQ + NO) * 8; e += 256) {
+        const bool isg = e < MQ * 8;
+        const Opnd &O = isg ? P.G : P.X;
+        const int c = 4 * (isg ? e : e - MQ * 8);
+        Coef cf;
+        load_coef(O, O.k0 + c, c < O.K ? 4 : 0, cf);
+        s_coef[e][0] = cf.a; s_coef[e][1] = cf.d; s_coef[e][2] = cf.b; s_coef[e][3] = cf.a2; s_coef[e][4] = cf.d2;
+    }
+    for (int e = tid; e < MQ * 32 * NO * 32; e += 256) s_dw[e] = 0.f;
+    __syncthreads();
+
+    float acc[MQ][4][NO][8];
+#pragma unroll
+    for (int a = 0; a < MQ; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int c = 0; c < NO; c++)
+#pragma unroll
+                for (int d = 0; d < 8; d++) acc[a][b][c][d] = 0.f;
+
+    const long n_groups = (P.rows + 3) / 4;
+    const long wstride = (long)gridDim.x * 8;
+    float4 ru[MQ + NO], rw[MQ + NO];                                   // raw pieces of the NEXT group (software prefetch)
+    auto fetch = [&](long grp) {
+        const long r = min(grp * 4 + li, P.rows - 1);
+#pragma unroll
+        for (int t = 0; t < MQ + NO; t++) {
+            const bool isg = t < MQ;
+            const Opnd &O = isg ? P.G : P.X;
+            const int c = 4 * (lj + 8 * (isg ? t : t - MQ));
+            if (c < O.K) narrow_load(O, r, c, ru[t], rw[t]);
+            else ru[t] = rw[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    long grp = (long)blockIdx.x * 8 + (tid >> 5);
+    if (grp < n_groups) fetch(grp);
+    for (; grp < n_groups; grp += wstride) {
+        // ---- transform this group's pieces (this lane: row li, quads lj + 8 t) ----
+        float4 tv[MQ + NO];
+        const bool row_ok = grp * 4 + li < P.rows;
+#pragma unroll
+        for (int t = 0; t < MQ + NO; t++) {
+            const bool isg = t < MQ;
+            const Opnd &O = isg ? P.G : P.X;
+            const int e = (isg ? t : MQ + (t - MQ)) * 8 + lj;
+            const int c = 4 * (lj + 8 * (isg ? t : t - MQ));
+            Coef cf;
+            cf.a = s_coef[e][0]; cf.d = s_coef[e][1]; cf.b = s_coef[e][2]; cf.a2 = s_coef[e][3]; cf.d2 = s_coef[e][4];
+            float4 v = xform(O.kind, ru[t], rw[t], cf);
+            if (!row_ok || c >= O.K) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            tv[t] = v;
+        }
+        if (grp + wstride < n_groups) fetch(grp + wstride);           // next group's loads fly during the outer products
+        // ---- 4 rows: dW block of this lane += g (4 MQ channels) x x (8 NO channels) ----
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            float g[MQ][4], x[NO][8];
+#pragma unroll
+            for (int a = 0; a < MQ; a++) {
+                const int src = rr * 8 + lj;                           // lane holding quad lj (+ 8 a) of row rr
+                g[a][0] = __shfl_sync(0xffffffffu, tv[a].x, src); g[a][1] = __shfl_sync(0xffffffffu, tv[a].y, src);
+                g[a][2] = __shfl_sync(0xffffffffu, tv[a].z, src); g[a][3] = __shfl_sync(0xffffffffu, tv[a].w, src);
+            }
+#pragma unroll
+            for (int c = 0; c < NO; c++) {
+                const int s0 = rr * 8 + 2 * li;                        // lanes holding quads 2 li, 2 li + 1 (+ 8 c) of row rr
+                x[c][0] = __shfl_sync(0xffffffffu, tv[MQ + c].x, s0); x[c][1] = __shfl_sync(0xffffffffu, tv[MQ + c].y, s0);
+                x[c][2] = __shfl_sync(0xffffffffu, tv[MQ + c].z, s0); x[c][3] = __shfl_sync(0xffffffffu, tv[MQ + c].w, s0);
+                x[c][4] = __shfl_sync(0xffffffffu, tv[MQ + c].x, s0 + 1); x[c][5] = __shfl_sync(0xffffffffu, tv[MQ + c].y, s0 + 1);
+                x[c][6] = __shfl_sync(0xffffffffu, tv[MQ + c].z, s0 + 1); x[c][7] = __shfl_sync(0xffffffffu, tv[MQ + c].w, s0 + 1);
+            }
+#pragma unroll
+            for (int a = 0; a < MQ; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+#pragma unroll
+                    for (int c = 0; c < NO; c++)
+#pragma unroll
+                        for (int d = 0; d < 8; d++) acc[a][b][c][d] = fmaf(g[a][b], x[c][d], acc[a][b][c][d]);
+        }
+    }
+    // ---- block reduction in shared memory, one global reduction per element and block ----
+    constexpr int NW = NO * 32;
+#pragma unroll
+    for (int a = 0; a < MQ; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int c = 0; c < NO; c++)
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    const int m = 4 * (lj + 8 * a) + b, n = 8 * (li + 4 * c) + d;
+                    atomicAdd(&s_dw[m * NW + n], acc[a][b][c][d]);
+                }
+    __syncthreads();
+    for (int e = tid; e < MQ * 32 * NW; e += 256) {
+        const int m = e / NW, n = e - m * NW;
+        if (m < P.M && n < P.N) atomicAdd(P.dW + (size_t)m * P.ldw + n, s_dw[e]);
+    }
+}
+
+// Returns 0 when the launch was made, -1 when the problem is not one for this kernel.
+int wgrad_narrow_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, float *dW, int ldw, cudaStream_t stream)
+{
+    const int M = G->K, N = X->K;
+    if (M > 64 || N > 64 || (M & 3) || (N & 3) || rows < 8192) return -1;
+    if (G->kind == RSB_OPND_GATHER) return -1;
+    auto wrap_ok = [](const Opnd &O) { return O.kind != RSB_OPND_AFFINE2 || ((O.k0 % O.ku) + O.K <= O.ku) || ((O.ku & 3) == 0); };
+    if (!wrap_ok(*G) || !wrap_ok(*X)) return -1;
+    NarrowParams P;
+    P.G = *G; P.X = *X; P.dW = dW; P.ldw = ldw; P.rows = rows; P.M = M; P.N = N;
+    const int mq = M > 32 ? 2 : 1, no = N > 32 ? 2 : 1;
+    const int blocks = rsb_sm_count() * ((mq * no == 1) ? 3 : (mq * no == 2 ? 2 : 1));
+    if (mq == 1 && no == 1) wgrad_narrow_kernel<1, 1><<<blocks, 256, 0, stream>>>(P);
+    else if (mq == 2 && no == 1) wgrad_narrow_kernel<2, 1><<<blocks, 256, 0, stream>>>(P);
+    else if (mq == 1 && no == 2) wgrad_narrow_kernel<1, 2><<<blocks, 256, 0, stream>>>(P);
+    else wgrad_narrow_kernel<2, 2><<<blocks, 256, 0, stream>>>(P);
+    RSB_CHECK_LAUNCH("wgrad_narrow_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+// RSB_WGRAD_TC=1: always the tensor-core weight-gradient kernel (A/B against the narrow-layer kernel)
+int g_wgrad_tc_only = [] { const char *v = getenv("RSB_WGRAD_TC"); return (v && v[0] && v[0] != '0') ? 1 : 0; }();
 int g_force_v1 = [] { const char *v = getenv("RSB_TC_V1"); return (v && v[0] && v[0] != '0') ? 1 : 0; }();
 
 bool opnd_tma_ok(const Opnd &O)
@@ -999,6 +1176,10 @@ int rsb_gemm_wgrad2_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, 
     if (!opnd_tma_ok(*G) || !opnd_tma_ok(*X)) return -1;
     if (G->kind == RSB_OPND_GATHER) return -1;           // only the X operand (the layer's input rows) is ever gathered
     if (rows + KC >= (1L << 31)) return -1;
+    if (!g_wgrad_tc_only) {                              // narrow layers over many rows: the fp32-pipe kernel
+        const int rn = wgrad_narrow_launch(rows, G, X, dW, ldw, stream);
+        if (rn >= 0) return rn;
+    }
     // AFFINE2 operands whose U tensor wraps (k % ku) inside the operand: every 32-channel box must stay inside one period
     auto wrap_ok = [](const Opnd &O) {
         if (O.kind != RSB_OPND_AFFINE2) return true;

@@ -149,7 +149,8 @@ def main():
              (300, 256, 272, "aff", "none"), (3000, 512, 256, "raw", "mask"), (3000, 256, 256, "aff", "mask"), (1000, 1024, 512, "raw", "mask")]
     for c in small:
         run_rows(*c, g)
-    smallw = [(1000, 64, 20, "aff", "raw"), (1000, 32, 64, "aff", "dual"), (2077, 64, 32, "raw", "bn"), (4000, 128, 128, "affwrap", "raw"),
+    smallw = [(9000, 32, 32, "aff", "dual"), (10001, 64, 20, "affwrap", "raw"), (20000, 64, 64, "raw", "bn"), (8200, 32, 64, "bn", "aff"),
+              (1000, 64, 20, "aff", "raw"), (1000, 32, 64, "aff", "dual"), (2077, 64, 32, "raw", "bn"), (4000, 128, 128, "affwrap", "raw"),
               (3000, 512, 272, "aff", "bn"), (999, 256, 144, "aff", "dual")]
     for c in smallw:
         run_wgrad(*c, g)
