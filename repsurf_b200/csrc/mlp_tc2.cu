@@ -883,9 +883,9 @@ __global__ void __launch_bounds__(THREADS2, 1) gemm_wgrad2_kernel(const __grid_c
 }
 
 // ============================================================================================================
-// dW for NARROW layers (M <= 64 gradient channels, N <= 64 input channels) on the fp32 pipe
+// dW for NARROW layers (M <= 32 gradient channels, N <= 32 input channels) on the fp32 pipe
 // ============================================================================================================
-// The sa1 weight gradients are [32..64] x [20..64] matrices reduced over 2.6 M rows: 1-2 kFLOP per 250-500 bytes of operands.
+// The narrowest sa1 weight gradients are 32 x 32 matrices reduced over 2.6 M rows: 1 kFLOP per 250-500 bytes of operands.
 // On the tensor core the gradient tile is padded to UMMA's M = 128: three quarters of every operand read from shared memory
 // feed accumulator rows nobody uses, and with the in-place transform's own traffic the kernel sits at 55-75 % of the SM's
 // shared-memory bandwidth (ncu l1tex throughput; profiles/r02_ncu_full_seg.md) at 0.27-0.46 of the HBM roofline, whatever the
@@ -1040,7 +1040,9 @@ __global__ void __launch_bounds__(256, (MQ * NO == 1) ? 3 : (MQ * NO == 2 ? 2 : 
 int wgrad_narrow_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, float *dW, int ldw, cudaStream_t stream)
 {
     const int M = G->K, N = X->K;
-    if (M > 64 || N > 64 || (M & 3) || (N & 3) || rows < 8192) return -1;
+    // measured (scripts/ab_gemm.py, 2.6 M rows): 32 x 32 0.47 -> 0.61 of the HBM roofline; from 64 x 20 up the M N / 32 FMAs per row
+    // and lane make the fp32 pipe the limit (64 x 32: 0.38 -> 0.30, 64 x 64: 0.60 -> 0.39), so only the 32 x 32 class comes here
+    if (M > 32 || N > 32 || (M & 3) || (N & 3) || rows < 8192) return -1;
     if (G->kind == RSB_OPND_GATHER) return -1;
     auto wrap_ok = [](const Opnd &O) { return O.kind != RSB_OPND_AFFINE2 || ((O.k0 % O.ku) + O.K <= O.ku) || ((O.ku & 3) == 0); };
     if (!wrap_ok(*G) || !wrap_ok(*X)) return -1;
@@ -1048,10 +1050,7 @@ int wgrad_narrow_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, flo
     P.G = *G; P.X = *X; P.dW = dW; P.ldw = ldw; P.rows = rows; P.M = M; P.N = N;
     const int mq = M > 32 ? 2 : 1, no = N > 32 ? 2 : 1;
     const int blocks = rsb_sm_count() * ((mq * no == 1) ? 3 : (mq * no == 2 ? 2 : 1));
-    if (mq == 1 && no == 1) wgrad_narrow_kernel<1, 1><<<blocks, 256, 0, stream>>>(P);
-    else if (mq == 2 && no == 1) wgrad_narrow_kernel<2, 1><<<blocks, 256, 0, stream>>>(P);
-    else if (mq == 1 && no == 2) wgrad_narrow_kernel<1, 2><<<blocks, 256, 0, stream>>>(P);
-    else wgrad_narrow_kernel<2, 2><<<blocks, 256, 0, stream>>>(P);
+    wgrad_narrow_kernel<1, 1><<<blocks, 256, 0, stream>>>(P);
     RSB_CHECK_LAUNCH("wgrad_narrow_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;
