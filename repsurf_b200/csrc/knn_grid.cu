@@ -15,10 +15,10 @@
 //     with the exact heap restatement over the whole cloud (knn_heap_replay_grid), as in query.cu.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int TARGET_PER_CELL = 8;
 constexpr int GRID_WARPS = 8;
 
 struct SegGrid {
@@ -38,6 +38,7 @@ struct GridParams {
     int *cursor;               // [n_total + b + 1]
     int *cid;                  // [n_total]
     float4 *sorted;            // [n_total]
+    float target_per_cell;     // average points per grid cell the geometry aims for (depends on k, see rsb_knnquery_grid)
 };
 
 __device__ __forceinline__ void seg_range(const GridParams &P, int s, int &c0, int &c1)
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(1024) grid_setup_kernel(GridParams P)
         g.cell_base = c0 + s;
         if (npts <= 0) { g.ox = g.oy = g.oz = 0.f; g.h = 1.f; g.inv_h = 1.f; g.gx = g.gy = g.gz = 1; P.seg[s] = g; return; }
         const float ex = fmaxf(hi[0] - lo[0], 1e-12f), ey = fmaxf(hi[1] - lo[1], 1e-12f), ez = fmaxf(hi[2] - lo[2], 1e-12f);
-        float h = cbrtf(ex * ey * ez * (float)TARGET_PER_CELL / (float)npts);
+        float h = cbrtf(ex * ey * ez * P.target_per_cell / (float)npts);
         h = fmaxf(h, 1e-6f * fmaxf(ex, fmaxf(ey, ez)));
         int gx, gy, gz;
         for (int it = 0; it < 64; it++) {
@@ -538,6 +539,13 @@ RSB_EXPORT int rsb_knnquery_grid(int packed, int heap, int b, int n, int m, int 
     unsigned char *w = static_cast<unsigned char *>(workspace);
     GridParams G = {};
     G.xyz = xyz; G.offset = packed ? offset : nullptr; G.b = b; G.n = n;
+    // Cell size by k: the search stops after the 27-cell neighbourhood when the k-th neighbour is closer than the nearest face of
+    // that cube (>= one cell edge h away).  In a uniform cloud with p points per cell the k nearest lie within
+    // h (3 k / (4 pi p))^(1/3): p ~ k / 2 puts them at ~0.8 h.  Fewer points per cell for small k mean fewer candidates
+    // (k = 3: ~70 instead of ~216), more for k = 32 avoid the 125-cell second ring (~1000 candidates).  The result is exact
+    // for any p; RSB_KNN_PPC overrides (tuning).
+    static const float ppc_env = [] { const char *v = getenv("RSB_KNN_PPC"); return v ? (float)atof(v) : 0.f; }();
+    G.target_per_cell = ppc_env > 0.f ? ppc_env : fminf(fmaxf(0.5f * (float)nsample, 2.5f), 24.f);
     G.seg = reinterpret_cast<SegGrid *>(w); w += align_up(sizeof(SegGrid) * (size_t)b, 256);
     G.bbox = reinterpret_cast<float *>(w); w += align_up(sizeof(float) * 6 * (size_t)b, 256);
     const size_t cells = (size_t)n_total + b + 1;
