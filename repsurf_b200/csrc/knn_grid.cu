@@ -263,8 +263,14 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
     const int qi = blockIdx.x * GRID_WARPS + warp;
     if (qi >= P.m_total) return;
     int s;
-    if (P.packed) { s = 0; while (qi >= P.new_offset[s]) s++; }
-    else s = qi / P.m_dense;
+    if (P.packed) {
+        // segment of the query: number of cumulative ends <= qi, 32 segments per ballot (one load instead of a dependent chain)
+        s = 0;
+        for (int b0 = 0; b0 < P.b; b0 += 32) {
+            const int e = b0 + lane < P.b ? __ldg(P.new_offset + b0 + lane) : 0x7fffffff;
+            s += __popc(__ballot_sync(0xffffffffu, qi >= e));
+        }
+    } else s = qi / P.m_dense;
     const SegGrid g = P.seg[s];
     const int k = P.k;
     const int index_base = P.packed ? 0 : g.cstart;
