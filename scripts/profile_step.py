@@ -13,7 +13,8 @@ W = bench.WORKLOADS[wl]
 host = bench.make_inputs(wl, W["clouds"], W["n"], 100, True)
 inp = [t.to(dev) for t in host]
 model = (RepSurfSeg() if wl == "seg" else RepSurfCls()).to(dev).train()
-crit = nn.CrossEntropyLoss() if wl == "seg" else SmoothClsLoss()
+from repsurf_b200.seg.loss import CrossEntropyLoss
+    crit = CrossEntropyLoss() if wl == "seg" else SmoothClsLoss()
 def step():
     model.zero_grad(set_to_none=True)
     if wl == "seg":
