@@ -349,6 +349,19 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # still warm-up, never timed: keep stepping until the caching allocator has stopped growing.  The geometry plan allocates
+    # on side streams (blocks return to their pool only after the consumer stream's recorded use), so the steady-state set of
+    # blocks can take a few more steps than W to appear; a cudaMalloc of a GB-sized block inside the timed region costs tens
+    # of milliseconds (seen once: 33 ms/step in the first pass against 20 ms in every later pass of the same process).
+    reserved = -1
+    for _ in range(12):
+        torch.cuda.synchronize()
+        now = torch.cuda.memory_reserved(dev)
+        if now == reserved:
+            break
+        reserved = now
+        step_resident()
+        step_resident()
     clocks = ClockSampler(local_rank)
     if full and rank == 0 and not os.environ.get("RSB_NO_CLOCKS"):
         clocks.start()
