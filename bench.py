@@ -435,6 +435,10 @@ def build_rooflines(per_entry, knn_work, ms_step, steps, workload):
         k, d = max(mine.items(), key=lambda kd: kd[1]["bytes"])
         t_ms = d["ms"] / d["n"]
         ach = d["bytes"] / (t_ms * 1e-3) / 1e9
+        if name == "rsb_gemm_wgrad" and "dW[" in k[1]:
+            mn = k[1].split("dW[")[1].split("]")[0].split("x")
+            if int(mn[0]) <= 32 and int(mn[1]) <= 32:
+                kern = "wgrad_narrow_kernel (fp32 pipe, register-blocked; the 32 x 32 class does not go to the tensor core)"
         rooflines[name] = {"kernel": kern, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                            "launch_ms": t_ms, "launch": k[1] + " (the shape that moves the most bytes)",
                            "algorithmic_bytes_per_launch": d["bytes"], "algorithmic_tflops": d["flops"] / (t_ms * 1e-3) / 1e12}
