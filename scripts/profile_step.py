@@ -14,7 +14,7 @@ host = bench.make_inputs(wl, W["clouds"], W["n"], 100, True)
 inp = [t.to(dev) for t in host]
 model = (RepSurfSeg() if wl == "seg" else RepSurfCls()).to(dev).train()
 from repsurf_b200.seg.loss import CrossEntropyLoss
-    crit = CrossEntropyLoss() if wl == "seg" else SmoothClsLoss()
+crit = CrossEntropyLoss() if wl == "seg" else SmoothClsLoss()
 def step():
     model.zero_grad(set_to_none=True)
     if wl == "seg":
