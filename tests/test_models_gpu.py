@@ -253,3 +253,30 @@ def test_reference_state_dict_keys_load_strict(golden_dir):
         got = {k: list(v.shape) for k, v in mine.state_dict().items()}
         assert sorted(got) == sorted(ref[name])
         assert got == ref[name]
+
+
+def test_execution_options_do_not_change_results(golden_dir):
+    """The geometry plan (FPS / kNN of all levels ahead on side streams) and the gather-fused first layer are scheduling /
+    data-movement choices: the network output must be bit-identical with either switched off."""
+    from repsurf_b200.models import RepSurfSeg
+    from repsurf_b200.seg import modules as M
+    g = np.load(os.path.join(golden_dir, "seg_10240_6000.npz"))
+    inp = [torch.from_numpy(g["coord"]).to(cuda), torch.from_numpy(g["feat"]).to(cuda), torch.from_numpy(g["offset"]).to(cuda)]
+    model = det_fill_(RepSurfSeg())
+    _no_dropout(model)
+    model = model.to(cuda).train()
+    for m in model.modules():
+        if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            m.momentum = 0.0                                   # keep the running buffers fixed across the repeated forwards
+    outs = {}
+    try:
+        for streams in (True, False):
+            for fuse in (True, False):
+                M.USE_SIDE_STREAMS, M.FUSE_GATHER = streams, fuse
+                np.random.seed(4321)
+                with torch.no_grad():
+                    outs[(streams, fuse)] = model(inp).clone()
+    finally:
+        M.USE_SIDE_STREAMS, M.FUSE_GATHER = True, True
+    ref = outs[(True, True)]
+    assert all(torch.equal(ref, o) for o in outs.values())
