@@ -19,6 +19,7 @@
 
 namespace {
 
+constexpr int GRID_STAGE = 320;     // float4 candidates per warp that a pass may stage in shared memory (5 KB)
 constexpr int GRID_WARPS = 8;
 
 struct SegGrid {
@@ -259,9 +260,20 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
 {
     __shared__ float heap_d[HEAP ? GRID_WARPS * 100 : 1];
     __shared__ int heap_i[HEAP ? GRID_WARPS * 100 : 1];
+    // per-warp staging area: the candidates of one pass (<= 32 cell ranges) are fetched into it by bulk copies (the TMA engine's
+    // 1-D mode: every range of the cell-sorted float4 array is a 16-byte aligned run), completion on the warp's mbarrier
+    __shared__ __align__(16) float4 stage[GRID_WARPS][GRID_STAGE];
+    __shared__ __align__(8) unsigned long long stage_bar[GRID_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * GRID_WARPS + warp;
     if (qi >= P.m_total) return;
+    const uint32_t bar = rsb_smem_addr(&stage_bar[warp]), stage_base = rsb_smem_addr(&stage[warp][0]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t stage_phase = 0;
     int s;
     if (P.packed) {
         // segment of the query: number of cumulative ends <= qi, 32 segments per ballot (one load instead of a dependent chain)
@@ -307,24 +319,51 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         n_cand += (unsigned)total;
         n_ranges += (unsigned)__popc(__ballot_sync(0xffffffffu, len > 0));
+        // passes that fit the staging area: one bulk copy per range, all in flight at once, then the candidates are read from
+        // shared memory as one contiguous array (no per-batch global-load latency, no search for a position's range)
+        const bool staged = total > 0 && total <= GRID_STAGE;
+        if (staged) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier reads of the area vs the copies that refill it
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)total * 16u) : "memory");
+            __syncwarp();
+            if (len > 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 stage_base + (uint32_t)(incl - len) * 16u), "l"(P.sorted + my_s), "r"((uint32_t)len * 16u), "r"(bar)
+                             : "memory");
+            uint32_t done;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(done) : "r"(bar), "r"(stage_phase) : "memory");
+            } while (!done);
+            stage_phase ^= 1u;
+        }
         for (int base = 0; base < total; base += 32) {
             const int pos = base + lane;
             const int j1 = 1, j = pos < total ? 0 : 1;            // "j < j1"  <=>  this lane holds a candidate
-            // range of this position: first lane whose inclusive prefix exceeds it (binary search over the warp's prefixes)
-            int slot = 0;
-#pragma unroll
-            for (int st = 16; st > 0; st >>= 1) {
-                const int v = __shfl_sync(0xffffffffu, incl, slot + st - 1);
-                if (v <= pos) slot += st;
-            }
-            slot = min(slot, 31);
-            const int rs = __shfl_sync(0xffffffffu, my_s, slot), rexcl = __shfl_sync(0xffffffffu, incl - len, slot);
             float d = CUDART_INF_F;
             int ci = 0;
-            if (j < j1) {
-                const float4 p = __ldg(P.sorted + rs + (pos - rexcl));
-                d = rsb_sqdist(qx, qy, qz, p.x, p.y, p.z);
-                ci = __float_as_int(p.w) - index_base;
+            if (staged) {
+                if (j < j1) {
+                    const float4 p = stage[warp][pos];
+                    d = rsb_sqdist(qx, qy, qz, p.x, p.y, p.z);
+                    ci = __float_as_int(p.w) - index_base;
+                }
+            } else {
+                // range of this position: first lane whose inclusive prefix exceeds it (binary search over the warp's prefixes)
+                int slot = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, slot + st - 1);
+                    if (v <= pos) slot += st;
+                }
+                slot = min(slot, 31);
+                const int rs = __shfl_sync(0xffffffffu, my_s, slot), rexcl = __shfl_sync(0xffffffffu, incl - len, slot);
+                if (j < j1) {
+                    const float4 p = __ldg(P.sorted + rs + (pos - rexcl));
+                    d = rsb_sqdist(qx, qy, qz, p.x, p.y, p.z);
+                    ci = __float_as_int(p.w) - index_base;
+                }
             }
             if constexpr (KPL == 1) {
                 unsigned long long ck = j < j1 ? knn_key(d, ci) : ~0ull;
