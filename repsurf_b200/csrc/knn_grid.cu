@@ -255,20 +255,22 @@ __device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, in
 }
 __device__ __forceinline__ unsigned long long knn_key(float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; }
 
-template <int KPL, bool HEAP>
+template <int KPL, bool HEAP, bool STAGED>
 __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
 {
     __shared__ float heap_d[HEAP ? GRID_WARPS * 100 : 1];
     __shared__ int heap_i[HEAP ? GRID_WARPS * 100 : 1];
     // per-warp staging area: the candidates of one pass (<= 32 cell ranges) are fetched into it by bulk copies (the TMA engine's
     // 1-D mode: every range of the cell-sorted float4 array is a 16-byte aligned run), completion on the warp's mbarrier
-    __shared__ __align__(16) float4 stage[GRID_WARPS][GRID_STAGE];
+    // (STAGED; measured on the S3DIS step: 2.64 ms -> 2.87 ms per step - the extra registers and shared memory cost a resident
+    // block per SM and the kernel is issue-bound, not latency-bound - so the default is the direct path: RSB_KNN_STAGE=1 selects this)
+    __shared__ __align__(16) float4 stage[STAGED ? GRID_WARPS : 1][STAGED ? GRID_STAGE : 1];
     __shared__ __align__(8) unsigned long long stage_bar[GRID_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * GRID_WARPS + warp;
     if (qi >= P.m_total) return;
-    const uint32_t bar = rsb_smem_addr(&stage_bar[warp]), stage_base = rsb_smem_addr(&stage[warp][0]);
-    if (lane == 0) {
+    const uint32_t bar = rsb_smem_addr(&stage_bar[warp]), stage_base = rsb_smem_addr(&stage[STAGED ? warp : 0][0]);
+    if (STAGED && lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
         n_ranges += (unsigned)__popc(__ballot_sync(0xffffffffu, len > 0));
         // passes that fit the staging area: one bulk copy per range, all in flight at once, then the candidates are read from
         // shared memory as one contiguous array (no per-batch global-load latency, no search for a position's range)
-        const bool staged = total > 0 && total <= GRID_STAGE;
+        const bool staged = STAGED && total > 0 && total <= GRID_STAGE;
         if (staged) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier reads of the area vs the copies that refill it
             if (lane == 0)
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32) knn_grid_kernel(GridQuery P)
             int ci = 0;
             if (staged) {
                 if (j < j1) {
-                    const float4 p = stage[warp][pos];
+                    const float4 p = stage[STAGED ? warp : 0][STAGED ? pos : 0];
                     d = rsb_sqdist(qx, qy, qz, p.x, p.y, p.z);
                     ci = __float_as_int(p.w) - index_base;
                 }
@@ -540,10 +542,12 @@ int launch_query(const GridQuery &Q, cudaStream_t stream)
 {
     const int blocks = RSB_DIVUP(Q.m_total, GRID_WARPS);
     if (blocks == 0) return 0;
-    if (Q.k <= 32) knn_grid_kernel<1, HEAP><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
-    else if (Q.k <= 64) knn_grid_kernel<2, HEAP><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
-    else if (Q.k <= 128) knn_grid_kernel<4, HEAP><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
-    else knn_grid_kernel<7, HEAP><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
+    static const bool stage = [] { const char *v = getenv("RSB_KNN_STAGE"); return v && v[0] && v[0] != '0'; }();
+    if (Q.k <= 32 && stage) knn_grid_kernel<1, HEAP, true><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
+    else if (Q.k <= 32) knn_grid_kernel<1, HEAP, false><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
+    else if (Q.k <= 64) knn_grid_kernel<2, HEAP, false><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
+    else if (Q.k <= 128) knn_grid_kernel<4, HEAP, false><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
+    else knn_grid_kernel<7, HEAP, false><<<blocks, GRID_WARPS * 32, 0, stream>>>(Q);
     RSB_CHECK_LAUNCH("knn_grid_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;
