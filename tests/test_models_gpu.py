@@ -280,3 +280,28 @@ def test_execution_options_do_not_change_results(golden_dir):
         M.USE_SIDE_STREAMS, M.FUSE_GATHER = True, True
     ref = outs[(True, True)]
     assert all(torch.equal(ref, o) for o in outs.values())
+
+
+def test_baseline_config_1_plumbing_case():
+    """BASELINE.json configs[0]: classification forward on ONE cloud of 128 points, eval mode (the reference runs this case on
+    the CPU with torch-native operators).  sa1 asks for 512 samples of 128 points: FPS then repeats index 0 once every point is
+    taken (reference CUDA semantics, reproduced by the C oracle); the CUDA model must agree with the oracle restatement."""
+    from oracle import model_ref as MR
+    from oracle import oracle as O
+    from repsurf_b200.cls import pointops as P
+    from repsurf_b200.models import RepSurfCls
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 128) * 2 - 1
+    xyz = x.transpose(1, 2).contiguous()
+    assert torch.equal(P.furthestsampling(xyz.to(cuda), 512).cpu(), O.fps_dense(xyz, 512))
+    ref = det_fill_(MR.ClsNet()).eval()
+    mine = det_fill_(RepSurfCls()).to(cuda).eval()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        want = ref(x)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        got = mine(x.to(cuda))
+    assert got.shape == (1, 15) and torch.isfinite(got).all()
+    ok, err = _close(got.cpu().numpy(), want.numpy(), rtol=2e-3)
+    assert ok, err
