@@ -334,13 +334,17 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        host_issue[fn.__name__] = (time.perf_counter() - t0) * 1e3 / steps     # host time to ISSUE a step (diagnostic)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -400,7 +404,8 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
     res = {"workload": wl["name"], "value": clouds_total / (ms_step * 1e-3), "ms_per_step": ms_step,
            "e2e": {"value": clouds_total / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-           "gpu_launches": int(launches), "clocks": clk, "per_entry": per_entry, "knn_work": knn_work, "ms_serial": ms_serial}
+           "gpu_launches": int(launches), "clocks": clk, "per_entry": per_entry, "knn_work": knn_work, "ms_serial": ms_serial,
+           "host_issue_ms": {k: round(v, 3) for k, v in host_issue.items()}}
     del model, opt, fg, devin
     torch.cuda.empty_cache()
     return res
@@ -593,6 +598,7 @@ def main():
                    "l2": "per-step working set (activations > 126 MB) exceeds L2; no explicit flush"},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": roof, "rooflines": rooflines,
         "entry_time_share": entry_share, "dominant_entry": dom[0] if dom else None, "clocks": r["clocks"],
+        "host_issue_ms_per_step": r["host_issue_ms"],
         "roofline_pass": {"note": "rooflines / entry_time_share come from a second pass of the same steps with the geometry plan's side "
                                   "streams off (every kernel timed alone, CUDA events around each C-ABI call); value / e2e are the "
                                   "overlapped production path", "ms_per_step_serialized": r["ms_serial"]},
