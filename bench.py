@@ -337,7 +337,13 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
     host_issue = {}
 
     def timed(fn, steps):
+        # the host needs ~12 of a step's ~20 ms to issue it: a full (generation-2) pass of Python's cyclic garbage collector
+        # inside the 10-step region (tens of ms over the autograd graphs of a step) makes those steps host-bound - seen twice
+        # as a 22 / 33 ms first pass.  Collect before, keep the collector off while timing (reference counting still frees).
+        import gc
+        gc.collect()
         barrier()
+        gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
@@ -345,6 +351,7 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
             fn()
         e1.record()
         host_issue[fn.__name__] = (time.perf_counter() - t0) * 1e3 / steps     # host time to ISSUE a step (diagnostic)
+        gc.enable()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
