@@ -133,14 +133,18 @@ def _ptr(t):
     return t.data_ptr()
 
 
+_FN = {}
+
+
 def call(name, *args):
     """Invoke a C-ABI entry on torch's current stream; tensors are passed as device pointers."""
-    L = lib()
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(lib(), name)
     conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else (ctypes.addressof(a) if isinstance(a, ctypes.Structure) else a)) for a in args]
-    stream = torch.cuda.current_stream().cuda_stream
-    rc = getattr(L, name)(*conv, stream)
+    rc = fn(*conv, torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
     if rc != 0:
-        raise RuntimeError(f"{name} failed (cudaError {rc}): {L.rsb_last_error().decode()}")
+        raise RuntimeError(f"{name} failed (cudaError {rc}): {lib().rsb_last_error().decode()}")
 
 
 def launch_count():
