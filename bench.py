@@ -94,7 +94,7 @@ class ClockSampler:
                     self.rows.append((float(sm), int(rs)))
                 except Exception:
                     pass
-                time.sleep(0.4)
+                time.sleep(0.02)      # ~10 samples over a 10-step region; in-process NVML queries cost ~0.1 ms each
         self.thread = threading.Thread(target=loop, daemon=True)
         self.thread.start()
 
@@ -347,10 +347,19 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
+        marks = []
         for _ in range(steps):
             fn()
+            if os.environ.get("RSB_STEP_MARKS"):
+                m = torch.cuda.Event(enable_timing=True)
+                m.record()
+                marks.append(m)
         e1.record()
         host_issue[fn.__name__] = (time.perf_counter() - t0) * 1e3 / steps     # host time to ISSUE a step (diagnostic)
+        if marks:
+            torch.cuda.synchronize()
+            ts = [e0.elapsed_time(m) for m in marks]
+            host_issue[fn.__name__ + "_marks"] = [round(b - a, 2) for a, b in zip([0.0] + ts[:-1], ts)]
         gc.enable()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -412,7 +421,7 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
            "e2e": {"value": clouds_total / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches), "clocks": clk, "per_entry": per_entry, "knn_work": knn_work, "ms_serial": ms_serial,
-           "host_issue_ms": {k: round(v, 3) for k, v in host_issue.items()}}
+           "host_issue_ms": {k: (v if isinstance(v, list) else round(v, 3)) for k, v in host_issue.items()}}
     del model, opt, fg, devin
     torch.cuda.empty_cache()
     return res
