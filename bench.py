@@ -110,8 +110,8 @@ class ClockSampler:
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
         reasons = sorted({k for _sm, rs in self.rows for k, bit in names.items() if rs & bit})
         sm = [r[0] for r in self.rows]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 # -------------------------------------------------------------------------------------------- per-entry timing
