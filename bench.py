@@ -342,8 +342,14 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
         # as a 22 / 33 ms first pass.  Collect before, keep the collector off while timing (reference counting still frees).
         import gc
         gc.collect()
-        barrier()
         gc.disable()
+        # three more untimed steps back to back with the timed ones: the GPU has just idled through the collector / NVML set-up
+        # above (tens to hundreds of ms on a freshly booted box), and the first pass after such a gap was sporadically 15-90 %
+        # slower than every later pass of the same process at unchanged reported clocks (host issue time unchanged, so the
+        # slowdown is on the device: memory / power state ramp).  Timing starts from a busy device.
+        for _ in range(3):
+            fn()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
