@@ -379,6 +379,9 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
     # on side streams (blocks return to their pool only after the consumer stream's recorded use), so the steady-state set of
     # blocks can take a few more steps than W to appear; a cudaMalloc of a GB-sized block inside the timed region costs tens
     # of milliseconds (seen once: 33 ms/step in the first pass against 20 ms in every later pass of the same process).
+    if workload == "seg":
+        from repsurf_b200.seg.modules import reserve_allocator_headroom
+        reserve_allocator_headroom(dev)          # one big cached block per stream: later requests split it instead of cudaMalloc
     reserved = -1
     for _ in range(12):
         torch.cuda.synchronize()
@@ -392,7 +395,9 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
     if full and rank == 0 and not os.environ.get("RSB_NO_CLOCKS"):
         clocks.start()
     _native.reset_launch_count()
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ms_step = timed(step_resident, args.steps)
+    device_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0      # cudaMalloc calls inside (diagnostic)
     launches = _native.launch_count()
     clk = clocks.stop() if (full and rank == 0) else None
     # per-entry kernel times for the rooflines: a SEPARATE pass of the same steps with the side streams of the geometry plan
@@ -427,7 +432,8 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
            "e2e": {"value": clouds_total / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches), "clocks": clk, "per_entry": per_entry, "knn_work": knn_work, "ms_serial": ms_serial,
-           "host_issue_ms": {k: (v if isinstance(v, list) else round(v, 3)) for k, v in host_issue.items()}}
+           "host_issue_ms": {k: (v if isinstance(v, list) else round(v, 3)) for k, v in host_issue.items()},
+           "device_allocs": int(device_allocs)}
     del model, opt, fg, devin
     torch.cuda.empty_cache()
     return res
@@ -620,7 +626,7 @@ def main():
                    "l2": "per-step working set (activations > 126 MB) exceeds L2; no explicit flush"},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": roof, "rooflines": rooflines,
         "entry_time_share": entry_share, "dominant_entry": dom[0] if dom else None, "clocks": r["clocks"],
-        "host_issue_ms_per_step": r["host_issue_ms"],
+        "host_issue_ms_per_step": r["host_issue_ms"], "cudaMalloc_calls_in_timed_region": r["device_allocs"],
         "roofline_pass": {"note": "rooflines / entry_time_share come from a second pass of the same steps with the geometry plan's side "
                                   "streams off (every kernel timed alone, CUDA events around each C-ABI call); value / e2e are the "
                                   "overlapped production path", "ms_per_step_serialized": r["ms_serial"]},

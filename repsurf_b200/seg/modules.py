@@ -57,6 +57,20 @@ def _side_streams(device):
     return _SIDE_STREAMS[key]
 
 
+def reserve_allocator_headroom(device, nbytes=4 << 30):
+    """Give torch's caching allocator one large free block on the main stream and on each side stream of the geometry plan.
+    Blocks are cached PER STREAM, and which side-stream blocks are reusable at a given moment depends on event timing, so a
+    training loop keeps hitting first-time cudaMalloc calls (device-wide stalls of tens of milliseconds for GB-sized blocks) for
+    many steps after the shapes have stopped changing; a big cached block is split instead.  Optional; results are unaffected."""
+    dev = torch.device(device)
+    streams = (torch.cuda.current_stream(dev),) + _side_streams(dev)
+    for st in streams:
+        with torch.cuda.stream(st):
+            x = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            del x
+    torch.cuda.synchronize(dev)
+
+
 def _sample(stride, center, offset, num_sector, training):
     """FPS of one level -> (fps_idx int64, new_center, new_offset); ref: segmentation/modules/repsurface_utils.py:24-33."""
     new_offset = strided_offsets(offset, stride)
