@@ -67,7 +67,8 @@ def reserve_allocator_headroom(device, nbytes=4 << 30):
     for st in streams:
         with torch.cuda.stream(st):
             x = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            del x
+            small = [torch.empty(512 << 10, dtype=torch.uint8, device=dev) for _ in range(64)]     # the <1 MB pool is separate
+            del x, small
     torch.cuda.synchronize(dev)
 
 

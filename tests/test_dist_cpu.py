@@ -30,7 +30,25 @@ def _worker(rank, world, port, q):
     model(clouds[lo:hi]).pow(2).mean().backward()
     flat = fg.allreduce_mean()
     assert all(torch.equal(p.grad.flatten(), v) for p, v in zip(fg.params, flat.split([p.numel() for p in fg.params])))
-    q.put((rank, flat.clone(), torch.cat([p.data.flatten() for p in model.parameters()])))
+    first = flat.clone()
+    # every run left while backward was still going (post-accumulate hooks), none had to be started by allreduce_mean
+    assert fg._hooked and len(fg._members) == 2
+    # gradient accumulation: a second backward after the runs have left is answered by one plain reduce of everything
+    fg.zero()
+    model(clouds[lo:hi]).pow(2).mean().backward()
+    assert all(h is not None for h in fg._handles)
+    model(clouds[lo:hi]).pow(2).mean().backward()
+    assert fg._dirty
+    twice = fg.allreduce_mean().clone()
+    assert torch.allclose(twice, 2 * first, rtol=1e-6, atol=1e-8)
+    # a parameter that takes no part in the step counts as zeros, like DDP
+    fg.zero()
+    model[0](clouds[lo:hi]).pow(2).mean().backward()
+    part = fg.allreduce_mean()
+    n_head = sum(p.numel() for p in model[2].parameters())
+    assert torch.count_nonzero(part[-n_head:]) == 0 and torch.count_nonzero(part[:-n_head]) > 0
+    assert all(p.grad is not None for p in fg.params)
+    q.put((rank, first, torch.cat([p.data.flatten() for p in model.parameters()])))
     dist.barrier()
     dist.destroy_process_group()
 
