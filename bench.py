@@ -319,10 +319,25 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
         opt.step()
         return loss
 
+    # the dense classification step has static shapes and is host-bound when issued eagerly (~300 launches of a few us):
+    # forward + backward + SGD are captured once in a CUDA graph and replayed (repsurf_b200/graph.py).  One process only -
+    # the N>1 run keeps the eager step with its overlapped all-reduce.  RSB_CLS_EAGER=1 forces the eager step.
+    gstep = None
+    if workload == "cls" and world == 1 and not os.environ.get("RSB_CLS_EAGER"):
+        from repsurf_b200.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, crit, opt, [devin[0]], devin[1])
+
+    def step_eager():
+        return fwd_bwd(devin)
+
     def step_resident():
+        if gstep is not None:
+            return gstep(gstep.static_in, gstep.static_tgt)
         return fwd_bwd(devin)
 
     def step_e2e():
+        if gstep is not None:                                # pinned host -> the graph's static buffers -> replay -> loss read
+            return float(gstep([host[0]], host[1]))
         inp = [t.to(dev, non_blocking=True) for t in host]
         if workload == "seg":
             PS.register_offsets(inp[2], host[2].tolist())   # the host already holds the offsets it uploads
@@ -398,7 +413,7 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
     mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ms_step = timed(step_resident, args.steps)
     device_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0      # cudaMalloc calls inside (diagnostic)
-    launches = _native.launch_count()
+    launches = _native.launch_count() if gstep is None else gstep.launches_per_step * args.steps   # replays bypass the counter
     clk = clocks.stop() if (full and rank == 0) else None
     # per-entry kernel times for the rooflines: a SEPARATE pass of the same steps with the side streams of the geometry plan
     # switched off, so that every launch is timed alone on one stream (CUDA events around each C-ABI call); in the throughput
@@ -408,12 +423,12 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
         from repsurf_b200.seg import modules as seg_modules
         timed_entries = None if os.environ.get("RSB_TIME_ALL_ENTRIES") else TIMED_ENTRIES
         seg_modules.USE_SIDE_STREAMS = False
-        step_resident()
+        step_eager()
         with EntryTimer(_native, timed_entries) as et:
-            ms_serial = timed(step_resident, args.steps)
+            ms_serial = timed(step_eager, args.steps)
         per_entry = et.summary()
         seg_modules.USE_SIDE_STREAMS = True
-        step_resident()
+        step_eager()
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -433,8 +448,8 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches), "clocks": clk, "per_entry": per_entry, "knn_work": knn_work, "ms_serial": ms_serial,
            "host_issue_ms": {k: (v if isinstance(v, list) else round(v, 3)) for k, v in host_issue.items()},
-           "device_allocs": int(device_allocs)}
-    del model, opt, fg, devin
+           "device_allocs": int(device_allocs), "cuda_graph": gstep is not None}
+    del model, opt, fg, devin, gstep
     torch.cuda.empty_cache()
     return res
 
@@ -622,7 +637,7 @@ def main():
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": wl["name"], "clouds_per_gpu": wl["clouds"], "points_per_cloud": wl["n"], "parallelism": f"dp{world}",
-                   "optimizer_step": "SGD momentum inside the timed region", "tf32": False,
+                   "optimizer_step": "SGD momentum inside the timed region", "tf32": False, "cuda_graph": r["cuda_graph"],
                    "l2": "per-step working set (activations > 126 MB) exceeds L2; no explicit flush"},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": roof, "rooflines": rooflines,
         "entry_time_share": entry_share, "dominant_entry": dom[0] if dom else None, "clocks": r["clocks"],
@@ -633,7 +648,7 @@ def main():
     }
     if second is not None:
         # BASELINE.json's other single-GPU configuration, same run, same timing rules (no per-entry breakdown)
-        out["secondary"] = {"metric": metric, "config": {"workload": second["workload"]}, "value": second["value"], "unit": "clouds/s",
+        out["secondary"] = {"metric": metric, "config": {"workload": second["workload"], "cuda_graph": second["cuda_graph"]}, "value": second["value"], "unit": "clouds/s",
                             "ms_per_step": second["ms_per_step"], "e2e": second["e2e"], "gpu_launches": second["gpu_launches"],
                             "n_gpus": world, "steps": args.steps}
     if not args.no_cpu_baseline:

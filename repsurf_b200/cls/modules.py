@@ -123,7 +123,10 @@ class UmbrellaSurfaceConstructor(nn.Module):
             idx = P.knnquery(self.k, xyz, xyz)                                  # [B,N,k] local ids, self first
             if self.random_inv:
                 # same draw as the reference: CPU generator, one per forward (recons_utils.py:49-51)
-                sign = (torch.randint(0, 2, (B, 1, 1)).float() * 2. - 1.).to(center.device)
+                if torch.cuda.is_current_stream_capturing():                    # a host draw would be frozen into the graph
+                    sign = torch.randint(0, 2, (B, 1, 1), device=center.device).float() * 2. - 1.
+                else:
+                    sign = (torch.randint(0, 2, (B, 1, 1)).float() * 2. - 1.).to(center.device)
             else:
                 sign = torch.ones(B, 1, 1, device=center.device)
             # one kernel: drop the query itself (:119), azimuth sort, triangles, normals, centroids, polar, NaN repair
