@@ -346,7 +346,14 @@ int rsb_fps_native_sample(int b, int c, int n, int m, const float *feat, const l
  *                    runs (= occupied voxels); scratch = ceil(n / 1024) ints                        voxelize_utils.py:50-51 (np.unique)
  * rsb_voxel_counts:  count[r], count_max[0] (pre-zeroed)
  * rsb_voxel_pick:    out[r] = order[start[r] + draw[r] % count[r]]                                  voxelize_utils.py:53-55
- * rsb_seed_distance: dist[i] = |coord[i] - coord[seed]|^2, un-fused fp32 like numpy                 data_util.py:47 */
+ * rsb_seed_distance: dist[i] = |coord[i] - coord[seed]|^2, un-fused fp32 like numpy                 data_util.py:47
+ * rsb_coord_max:     out3 (pre-set to -inf) = column maxima of coord [n,3]
+ * rsb_voxel_keys_ravel: key[i] = ravel_hash_vec(floor(coord / voxel_size))[i] (rank inside the occupied box)   voxelize_utils.py:20-35, :44
+ * whole-scene crop planner (segmentation/tool/test_s3dis.py:143-158, data_process):
+ * rsb_argmin_f64:    work[1] = index of the FIRST smallest element of v [n] (np.argmin; NaN-free input), work = 2 x uint64   :145
+ * rsb_seed_distance_dev: rsb_seed_distance with the seed index read from device memory               :146
+ * rsb_crop_update:   priority[crop] += (1 - dist[crop] / dist[crop[m-1]])^2 (fp32, added in fp64), covered[crop] = 1,
+ *                    *n_covered += rows covered for the first time; crop = m distinct rows in ascending distance   :150-158 */
 int rsb_coord_min(long n, const float *coord, float *out3, cudaStream_t stream);
 int rsb_voxel_keys(long n, const float *coord, const float *cmin, float voxel_size, long long *key, cudaStream_t stream);
 int rsb_voxel_runs(long n, const long long *sorted_key, int *scratch, int *start, int *scalars, cudaStream_t stream);
@@ -354,6 +361,13 @@ int rsb_voxel_counts(int n_runs, long n, const int *start, int *count, int *coun
 int rsb_voxel_pick(int n_runs, const int *start, const int *count, const long long *draw, const long long *order,
                    long long *out, cudaStream_t stream);
 int rsb_seed_distance(long n, const float *coord, long seed, float *dist, cudaStream_t stream);
+int rsb_coord_max(long n, const float *coord, float *out3, cudaStream_t stream);
+int rsb_voxel_keys_ravel(long n, const float *coord, const float *cmin, const float *cmax, float voxel_size, long long *key,
+                         cudaStream_t stream);
+int rsb_argmin_f64(long n, const double *v, unsigned long long *work, cudaStream_t stream);
+int rsb_seed_distance_dev(long n, const float *coord, const unsigned long long *seed, float *dist, cudaStream_t stream);
+int rsb_crop_update(int m, const long long *crop, const float *dist, double *priority, int *covered, int *n_covered,
+                    cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,11 @@ _SIGS = {
     "rsb_voxel_counts": [_i, _l, _p, _p, _p],
     "rsb_voxel_pick": [_i, _p, _p, _p, _p, _p],
     "rsb_seed_distance": [_l, _p, _l, _p],
+    "rsb_coord_max": [_l, _p, _p],
+    "rsb_voxel_keys_ravel": [_l, _p, _p, _p, _f, _p],
+    "rsb_argmin_f64": [_l, _p, _p],
+    "rsb_seed_distance_dev": [_l, _p, _p, _p],
+    "rsb_crop_update": [_i, _p, _p, _p, _p, _p],
     "rsb_point_table": [_l, _i, _i, _i, _p, _p, _p, _p],
     "rsb_cross_entropy_forward": [_l, _i, _p, _i, _p, ctypes.c_longlong, _p, _i, _p, _p],
     "rsb_cross_entropy_backward": [_l, _p, _p, _p],

@@ -3,8 +3,11 @@
 //   segmentation/modules/voxelize_utils.py:4-17    fnv_hash_vec   ("FNV64-1A": h = basis; per column h *= prime, h ^= value)
 //   segmentation/modules/voxelize_utils.py:38-58   voxelize       (floor(coord / voxel_size) -> key -> sort -> one point per voxel)
 //   segmentation/util/data_util.py:45-51           nearest crop   (voxel_max points closest to a seed point)
-// Kernels: per-column minimum, voxel keys, run detection over the sorted keys (flags -> block scan -> compaction), the
-// per-voxel pick, squared distance to a seed.  The 64-bit key sort and the distance sort between them are cub radix sorts
+//   segmentation/modules/voxelize_utils.py:20-35   ravel_hash_vec (row-major rank of the voxel inside the occupied bounding box)
+//   segmentation/tool/test_s3dis.py:131-159        data_process   (overlapping nearest crops until every point is covered)
+// Kernels: per-column minimum / maximum, voxel keys (FNV and ravel), run detection over the sorted keys (flags -> block scan ->
+// compaction), the per-voxel pick, squared distance to a seed (host- or device-resident seed index), first-occurrence argmin of
+// a float64 array, the coverage update of the crop planner.  The 64-bit key sort and the distance sort between them are cub radix sorts
 // (through torch.sort, stable) - the one library primitive of this path.  All kernels are single-pass and HBM-bound.
 #include "common.cuh"
 #include <math_constants.h>
@@ -21,10 +24,20 @@ inline int dp_grid(long work)
     return (int)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
+// float atomics through the integer orderings of the IEEE bit patterns.  `v + 0.f` turns -0.0 into +0.0 first: the pattern of
+// -0.0 is INT_MIN, which would win a signed atomicMin against every negative number (and lose every atomicMax)
 __device__ __forceinline__ void dp_atomic_min(float *a, float v)
 {
+    v = __fadd_rn(v, 0.f);
     if (v >= 0.f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(v));
     else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+
+__device__ __forceinline__ void dp_atomic_max(float *a, float v)
+{
+    v = __fadd_rn(v, 0.f);
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
 }
 
 // out3 (pre-set to +inf) = column minima of coord [n,3]
@@ -39,6 +52,44 @@ __global__ void __launch_bounds__(DP_TPB) coord_min_kernel(long n, const float *
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
         if ((threadIdx.x & 31) == 0 && lo[a] < CUDART_INF_F) dp_atomic_min(out3 + a, lo[a]);
+    }
+}
+
+// out3 (pre-set to -inf) = column maxima of coord [n,3]
+__global__ void __launch_bounds__(DP_TPB) coord_max_kernel(long n, const float *__restrict__ coord, float *__restrict__ out3)
+{
+    float hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (long i = blockIdx.x * (long)DP_TPB + threadIdx.x; i < n; i += (long)gridDim.x * DP_TPB)
+#pragma unroll
+        for (int a = 0; a < 3; a++) hi[a] = fmaxf(hi[a], __ldg(coord + i * 3 + a));
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        if ((threadIdx.x & 31) == 0 && hi[a] > -CUDART_INF_F) dp_atomic_max(out3 + a, hi[a]);
+    }
+}
+
+// ravel_hash_vec (voxelize_utils.py:20-35): d = floor(coord / voxel_size) - min over the cloud of the same (floor and the fp32
+// division are monotone, so that minimum is floor(cmin / voxel_size), likewise the maximum); extent e_a = max d_a + 1;
+// key = (d_0 * e_1 + d_1) * e_2 + d_2 in uint64.  Keys of a real cloud stay far below 2^63, so they sort as signed numbers.
+__global__ void __launch_bounds__(DP_TPB) voxel_key_ravel_kernel(long n, const float *__restrict__ coord, const float *__restrict__ cmin,
+                                                                 const float *__restrict__ cmax, float voxel_size,
+                                                                 long long *__restrict__ key)
+{
+    float lo[3];
+    unsigned long long ext[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        lo[a] = floorf(__fdiv_rn(__ldg(cmin + a), voxel_size));
+        ext[a] = (unsigned long long)__fsub_rn(floorf(__fdiv_rn(__ldg(cmax + a), voxel_size)), lo[a]) + 1ull;
+    }
+    for (long i = blockIdx.x * (long)DP_TPB + threadIdx.x; i < n; i += (long)gridDim.x * DP_TPB) {
+        unsigned long long d[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+            d[a] = (unsigned long long)__fsub_rn(floorf(__fdiv_rn(__ldg(coord + i * 3 + a), voxel_size)), lo[a]);
+        key[i] = (long long)((d[0] * ext[1] + d[1]) * ext[2] + d[2]);
     }
 }
 
@@ -181,6 +232,74 @@ __global__ void __launch_bounds__(DP_TPB) seed_dist_kernel(long n, const float *
     }
 }
 
+// same with the seed index read from device memory (the crop planner's argmin result never visits the host)
+__global__ void __launch_bounds__(DP_TPB) seed_dist_dev_kernel(long n, const float *__restrict__ coord,
+                                                               const unsigned long long *__restrict__ seed_p, float *__restrict__ d)
+{
+    const long seed = (long)__ldg(seed_p);
+    if (seed < 0 || seed >= n) return;
+    const float sx = __ldg(coord + seed * 3), sy = __ldg(coord + seed * 3 + 1), sz = __ldg(coord + seed * 3 + 2);
+    for (long i = blockIdx.x * (long)DP_TPB + threadIdx.x; i < n; i += (long)gridDim.x * DP_TPB) {
+        const float dx = __fsub_rn(__ldg(coord + i * 3), sx), dy = __fsub_rn(__ldg(coord + i * 3 + 1), sy),
+                    dz = __fsub_rn(__ldg(coord + i * 3 + 2), sz);
+        d[i] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    }
+}
+
+// ---- first-occurrence argmin of a float64 array (np.argmin), two passes over work[2] = {smallest key, its first index} -------
+// order-preserving map of a double onto uint64: negative -> all bits flipped, non-negative -> sign bit set
+__device__ __forceinline__ unsigned long long dp_f64_key(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(DP_TPB) argmin_key_kernel(long n, const double *__restrict__ v, unsigned long long *__restrict__ work)
+{
+    unsigned long long best = ~0ull;
+    for (long i = blockIdx.x * (long)DP_TPB + threadIdx.x; i < n; i += (long)gridDim.x * DP_TPB) {
+        const unsigned long long k = dp_f64_key(v[i]);
+        best = k < best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(work, best);
+}
+
+__global__ void __launch_bounds__(DP_TPB) argmin_index_kernel(long n, const double *__restrict__ v, unsigned long long *__restrict__ work)
+{
+    const unsigned long long want = work[0];
+    for (long i = blockIdx.x * (long)DP_TPB + threadIdx.x; i < n; i += (long)gridDim.x * DP_TPB)
+        if (dp_f64_key(v[i]) == want) atomicMin(work + 1, (unsigned long long)i);
+}
+
+// ---- coverage update of the crop planner (test_s3dis.py:146-153) -------------------------------------------------------------
+// crop [m] = the rows of this crop in ascending distance, dist [n] = squared distances of ALL rows to the seed:
+// priority[crop] += (1 - dist[crop] / max(dist[crop]))^2 (fp32 arithmetic, added to the float64 priorities like numpy does),
+// covered[crop] = 1, *n_covered += rows covered for the first time.  Rows of one crop are distinct.
+__global__ void __launch_bounds__(DP_TPB) crop_update_kernel(int m, const long long *__restrict__ crop, const float *__restrict__ dist,
+                                                             double *__restrict__ priority, int *__restrict__ covered,
+                                                             int *__restrict__ n_covered)
+{
+    const float dmax = __ldg(dist + crop[m - 1]);
+    int fresh = 0;
+    for (int j = blockIdx.x * DP_TPB + threadIdx.x; j < m; j += gridDim.x * DP_TPB) {
+        const long long r = crop[j];
+        const float t = __fsub_rn(1.f, __fdiv_rn(__ldg(dist + r), dmax));
+        priority[r] += (double)__fmul_rn(t, t);
+        if (covered[r] == 0) {
+            covered[r] = 1;
+            fresh++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_covered, fresh);
+}
+
 }  // namespace
 
 RSB_EXPORT int rsb_coord_min(long n, const float *coord, float *out3, cudaStream_t stream)
@@ -242,6 +361,58 @@ RSB_EXPORT int rsb_seed_distance(long n, const float *coord, long seed, float *d
     RSB_REQUIRE(n >= 1 && seed >= 0 && seed < n, "bad seed");
     seed_dist_kernel<<<dp_grid(n), DP_TPB, 0, stream>>>(n, coord, seed, dist);
     RSB_CHECK_LAUNCH("seed_dist_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+RSB_EXPORT int rsb_coord_max(long n, const float *coord, float *out3, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    coord_max_kernel<<<dp_grid(n), DP_TPB, 0, stream>>>(n, coord, out3);
+    RSB_CHECK_LAUNCH("coord_max_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+RSB_EXPORT int rsb_voxel_keys_ravel(long n, const float *coord, const float *cmin, const float *cmax, float voxel_size, long long *key,
+                                    cudaStream_t stream)
+{
+    RSB_REQUIRE(voxel_size > 0.f, "voxel_size must be positive");
+    if (n <= 0) return 0;
+    voxel_key_ravel_kernel<<<dp_grid(n), DP_TPB, 0, stream>>>(n, coord, cmin, cmax, voxel_size, key);
+    RSB_CHECK_LAUNCH("voxel_key_ravel_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+RSB_EXPORT int rsb_seed_distance_dev(long n, const float *coord, const unsigned long long *seed, float *dist, cudaStream_t stream)
+{
+    RSB_REQUIRE(n >= 1 && seed != nullptr, "bad seed");
+    seed_dist_dev_kernel<<<dp_grid(n), DP_TPB, 0, stream>>>(n, coord, seed, dist);
+    RSB_CHECK_LAUNCH("seed_dist_dev_kernel");
+    RSB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+// work: two uint64 on the device (any content); on return work[1] = index of the first smallest element of v [n] (NaN-free input)
+RSB_EXPORT int rsb_argmin_f64(long n, const double *v, unsigned long long *work, cudaStream_t stream)
+{
+    RSB_REQUIRE(n >= 1 && work != nullptr, "bad size");
+    RSB_CUDA(cudaMemsetAsync(work, 0xFF, 2 * sizeof(unsigned long long), stream));
+    argmin_key_kernel<<<dp_grid(n), DP_TPB, 0, stream>>>(n, v, work);
+    RSB_CHECK_LAUNCH("argmin_key_kernel");
+    argmin_index_kernel<<<dp_grid(n), DP_TPB, 0, stream>>>(n, v, work);
+    RSB_CHECK_LAUNCH("argmin_index_kernel");
+    RSB_COUNT_LAUNCH(2);
+    return 0;
+}
+
+RSB_EXPORT int rsb_crop_update(int m, const long long *crop, const float *dist, double *priority, int *covered, int *n_covered,
+                               cudaStream_t stream)
+{
+    if (m <= 0) return 0;
+    crop_update_kernel<<<dp_grid(m), DP_TPB, 0, stream>>>(m, crop, dist, priority, covered, n_covered);
+    RSB_CHECK_LAUNCH("crop_update_kernel");
     RSB_COUNT_LAUNCH(1);
     return 0;
 }

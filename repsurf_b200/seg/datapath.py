@@ -32,15 +32,27 @@ def fnv_hash_vec(coord, voxel_size):
     return _keys(coord.contiguous(), voxel_size) ^ torch.tensor(-2 ** 63, dtype=torch.int64, device=coord.device)
 
 
-def voxelize(coord, voxel_size=0.05, hash_type='fnv', mode=0):
-    """coord [n,3] float32 (device).  mode 0 (train): int64 [n_voxels] = one randomly chosen point per occupied voxel, voxels
-    in ascending key order (voxelize_utils.py:53-56).  mode 1 (val): (idx_sort int64 [n], count int32 [n_voxels])."""
-    if hash_type != 'fnv':
-        raise NotImplementedError("only the default FNV hash of the reference's pipeline is implemented")
+def ravel_hash_vec(coord, voxel_size):
+    """Keys of voxelize_utils.py:20-35 for floor(coord / voxel_size): the row-major rank of a point's voxel inside the
+    bounding box of the occupied voxels, int64 [n] (device)."""
+    coord = coord.contiguous()
+    n = coord.shape[0]
+    cmin = torch.full((3,), float("inf"), dtype=torch.float32, device=coord.device)
+    cmax = torch.full((3,), float("-inf"), dtype=torch.float32, device=coord.device)
+    N.call("rsb_coord_min", n, coord, cmin)
+    N.call("rsb_coord_max", n, coord, cmax)
+    key = torch.empty(n, dtype=torch.int64, device=coord.device)
+    N.call("rsb_voxel_keys_ravel", n, coord, cmin, cmax, float(voxel_size), key)
+    return key
+
+
+def voxel_runs(coord, voxel_size, hash_type='fnv'):
+    """Sort the points by voxel key: (idx_sort int64 [n], count int32 [n_voxels], start int32 [>= n_voxels] = first sorted
+    position of every voxel, largest count).  One read-back (the number of occupied voxels sizes what follows)."""
     coord = coord.contiguous()
     n = coord.shape[0]
     dev = coord.device
-    key = _keys(coord, voxel_size)
+    key = ravel_hash_vec(coord, voxel_size) if hash_type == 'ravel' else _keys(coord, voxel_size)
     key_sort, idx_sort = torch.sort(key, stable=True)            # cub radix sort; stable = ascending index inside a voxel
     scratch = torch.empty((n + 1023) // 1024, dtype=torch.int32, device=dev)
     start = torch.empty(n, dtype=torch.int32, device=dev)
@@ -49,11 +61,19 @@ def voxelize(coord, voxel_size=0.05, hash_type='fnv', mode=0):
     n_vox = int(scalars[0])                                       # read-back: sizes everything that follows
     count = torch.empty(n_vox, dtype=torch.int32, device=dev)
     N.call("rsb_voxel_counts", n_vox, n, start, count, scalars[1:2])
+    return idx_sort, count, start, int(scalars[1])
+
+
+def voxelize(coord, voxel_size=0.05, hash_type='fnv', mode=0):
+    """coord [n,3] float32 (device).  mode 0 (train): int64 [n_voxels] = one randomly chosen point per occupied voxel, voxels
+    in ascending key order (voxelize_utils.py:53-56).  mode 1 (val): (idx_sort int64 [n], count int32 [n_voxels]).
+    hash_type 'fnv' (the pipeline's default) or 'ravel', as in the reference."""
+    idx_sort, count, start, cmax = voxel_runs(coord, voxel_size, hash_type)
     if mode != 0:
         return idx_sort, count
-    cmax = int(scalars[1])
-    draw = torch.from_numpy(np.random.randint(0, cmax, n_vox)).to(dev)          # same draw as voxelize_utils.py:53
-    out = torch.empty(n_vox, dtype=torch.int64, device=dev)
+    n_vox = count.shape[0]
+    draw = torch.from_numpy(np.random.randint(0, cmax, n_vox)).to(coord.device)          # same draw as voxelize_utils.py:53
+    out = torch.empty(n_vox, dtype=torch.int64, device=coord.device)
     N.call("rsb_voxel_pick", n_vox, start, count, draw, idx_sort, out)
     return out
 

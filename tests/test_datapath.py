@@ -44,6 +44,49 @@ def test_restatement_matches_reference_functions():
         pick = V.voxelize(coord - coord.min(0), 0.04)
         keys = D.fnv_hash_vec(disc)
         assert len(pick) == len(ref_count) and len(np.unique(keys[pick])) == len(pick)
+        # hash_type='ravel': keys bit for bit (also for a cloud that does not start at the origin), same voxel sizes
+        for c in (coord - coord.min(0), coord - np.float32(1.7)):
+            d = np.floor(c / np.float32(0.04))
+            assert np.array_equal(V.ravel_hash_vec(d), D.ravel_hash_vec(d))
+        rs, rc = V.voxelize(coord - coord.min(0), 0.04, hash_type='ravel', mode=1)
+        ms, mc = D.voxelize(coord - coord.min(0), 0.04, hash_type='ravel', mode=1)
+        assert np.array_equal(rc, mc) and np.array_equal(np.sort(rc), np.sort(ref_count))
+
+
+def test_scene_crop_plan_matches_reference_data_process():
+    """data_load's voxel parts and data_process's covering crops (segmentation/tool/test_s3dis.py:114-159) against the
+    UNMODIFIED reference functions, same numpy seed.  Rows whose fp32 squared distances to a seed tie exactly come out of the
+    reference's unstable argsort in either order (seen: a swapped pair in 13 of 117 crops), so crops are compared as row sets plus
+    position-wise agreement; needs /root/reference."""
+    import types
+    from oracle import ref_loader as RL
+    if not RL.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    coord, feat, _ = _scan(30000, 4)
+    with RL.RefTree("seg") as t:
+        T = t.imp("tool.test_s3dis")
+        T.args = types.SimpleNamespace(voxel_size=0.04, voxel_max=3000, data_norm='mean', color_mean=None, color_std=None)
+        idx_sort, count = T.voxelize(coord - np.min(coord, 0), 0.04, mode=1)
+        ref_parts = [idx_sort[np.cumsum(np.insert(count, 0, 0)[0:-1]) + i % count] for i in range(count.max())]
+        my_parts = D.scene_parts(coord, 0.04)
+        assert len(ref_parts) == len(my_parts) and len(my_parts) >= 2
+        assert sorted(np.unique(np.concatenate(my_parts))) == list(range(coord.shape[0]))      # every point is in some part
+        for a, b in zip(ref_parts, my_parts):
+            # same voxels in the same order; which MEMBER is i-th in a voxel is the unstable argsort's choice
+            assert a.shape == b.shape
+        np.random.seed(9)
+        ri, rc, rf, ro = T.data_process(coord.copy(), feat.copy(), my_parts)
+        np.random.seed(9)
+        mi, mc, mf, mo = D.data_process(coord, feat, my_parts, 3000)
+    assert ro == mo and len(ri) == len(mi) and len(mi) > len(my_parts)
+    same = 0
+    for a, b, ca, cb, fa, fb in zip(ri, mi, rc, mc, rf, mf):
+        assert np.array_equal(np.sort(a), np.sort(b))                  # the same rows in every crop, crop after crop
+        eq = a == b
+        assert eq.mean() > 0.99                                        # in the same order except inside distance ties
+        assert np.array_equal(ca[eq], cb[eq]) and np.array_equal(fa[eq], fb[eq])
+        same += int(eq.all())
+    assert same >= len(ri) // 2                                      # most crops have no tie at all
 
 
 @pytest.mark.gpu
@@ -91,3 +134,35 @@ def test_device_data_prepare_and_collate_match_restatement():
     from repsurf_b200.models import RepSurfSeg
     out = RepSurfSeg().to(cuda).eval()([coord, feat, offset])
     assert out.shape == (coord.shape[0], 13) and torch.isfinite(out).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shift", [0.0, 1.7])
+def test_device_ravel_hash_matches_restatement(shift):
+    from repsurf_b200.seg import datapath as G
+    cuda = torch.device("cuda")
+    coord, _, _ = _scan(120000, 6)
+    c0 = coord - coord.min(0) if shift == 0.0 else coord - np.float32(shift)
+    dc = torch.from_numpy(c0).to(cuda)
+    disc = np.floor(c0 / np.float32(0.04))
+    assert np.array_equal(G.ravel_hash_vec(dc, 0.04).cpu().numpy().view(np.uint64), D.ravel_hash_vec(disc))
+    idx_sort, count = G.voxelize(dc, 0.04, hash_type='ravel', mode=1)
+    w_sort, w_count = D.voxelize(c0, 0.04, hash_type='ravel', mode=1)
+    assert np.array_equal(idx_sort.cpu().numpy(), w_sort) and np.array_equal(count.cpu().numpy(), w_count)
+    np.random.seed(5)
+    got = G.voxelize(dc, 0.04, hash_type='ravel').cpu().numpy()
+    np.random.seed(5)
+    assert np.array_equal(got, D.voxelize(c0, 0.04, hash_type='ravel'))
+
+
+@pytest.mark.gpu
+def test_device_column_extrema_with_negative_zero():
+    """-0.0 among negative coordinates: the float atomics must not take its bit pattern (INT_MIN) for the minimum"""
+    from repsurf_b200 import _native as N
+    cuda = torch.device("cuda")
+    c = torch.tensor([[-5.0, 2.0, -0.0], [-0.0, -3.0, -1.0], [4.0, -0.0, -2.0]], device=cuda).repeat(400, 1).contiguous()
+    lo = torch.full((3,), float("inf"), device=cuda)
+    hi = torch.full((3,), float("-inf"), device=cuda)
+    N.call("rsb_coord_min", c.shape[0], c, lo)
+    N.call("rsb_coord_max", c.shape[0], c, hi)
+    assert lo.tolist() == [-5.0, -3.0, -2.0] and hi.tolist() == [4.0, 2.0, 0.0]

@@ -119,6 +119,50 @@ def test_scene_inference_loop_runs_eval_model_on_crops():
     assert torch.equal(S.scene_inference(model, coords, feats, crops, n, 13, batch_size=2, filter_k=32, coord_all=xyz), lab)
 
 
+def test_argmin_f64_is_numpy_argmin():
+    """first occurrence among equal minima, negative and positive values"""
+    from repsurf_b200 import _native as N
+    r = np.random.RandomState(0)
+    for n, dup in ((1, False), (77, True), (100_003, True), (1_000_000, False)):
+        v = r.randn(n) if n != 77 else np.abs(r.randn(n))
+        if dup:
+            v[[n // 3, n // 2, n - 1]] = v.min() - 1.0              # three equal minima: the first one wins
+        work = torch.empty(2, dtype=torch.int64, device=cuda)
+        N.call("rsb_argmin_f64", n, torch.from_numpy(v).to(cuda), work)
+        assert int(work[1]) == int(np.argmin(v))
+
+
+def test_scene_parts_and_crop_plan_match_restatement():
+    """data_load / data_process of segmentation/tool/test_s3dis.py:114-159 on the device against the numpy restatement (which
+    tests/test_datapath.py pins to the unmodified reference functions): same parts, same crops in the same order, same rows."""
+    from oracle import datapath_ref as D
+    from repsurf_b200.seg import scene as S
+    n = 150_000
+    xyz = _room(n, 11)
+    xyz = (xyz * torch.tensor([0.2, 0.2, 1.0])).contiguous()               # 6 x 4 x 3 m: several points per 4 cm voxel
+    feat = (torch.rand(n, 3, generator=torch.Generator().manual_seed(12)) * 255).contiguous()
+    c_np, f_np = xyz.numpy(), feat.numpy()
+    parts = S.scene_parts(xyz.to(cuda), 0.04)
+    want_parts = D.scene_parts(c_np, 0.04)
+    assert len(parts) == len(want_parts) >= 2
+    for a, b in zip(parts, want_parts):
+        assert np.array_equal(a.cpu().numpy(), b)
+    np.random.seed(21)
+    gi, gc, gf, go = S.data_process(xyz.to(cuda), feat.to(cuda), parts, 20_000)
+    np.random.seed(21)
+    wi, wc, wf, wo = D.data_process(c_np, f_np, want_parts, 20_000)
+    assert go == wo and len(gi) == len(wi) > len(parts) and max(go) == 20_000
+    for a, b in zip(gi, wi):
+        assert np.array_equal(a.cpu().numpy(), b)                           # scene rows of every crop, in order
+    for a, b in zip(gf, wf):
+        assert np.array_equal(a.cpu().numpy(), (b).astype(np.float32))
+    for a, b in zip(gc, wc):
+        assert np.abs(a.cpu().numpy() - b).max() < 1e-5                     # centring: fp64 mean here, fp32 in numpy
+    covered = torch.zeros(n, dtype=torch.bool)
+    covered[torch.cat([i.cpu() for i in gi])] = True
+    assert bool(covered.all())                                              # every scene point receives at least one vote
+
+
 @pytest.mark.parametrize("rows,nc,ignore", [(50_000, 13, None), (4097, 13, 255), (1000, 20, 3)])
 def test_cross_entropy_matches_torch(rows, nc, ignore):
     """seg/loss.CrossEntropyLoss (one kernel: value + gradient) against nn.CrossEntropyLoss in fp64, on the row-padded logits
