@@ -154,3 +154,17 @@ def scene_inference(model, coord_parts, feat_parts, idx_parts, n_points, num_cla
     if filter_k:
         label = label_median(coord_all.to(dev).contiguous(), label, filter_k)
     return label
+
+
+def infer_scene(model, coord, feat, num_class, voxel_size=0.04, voxel_max=80000, batch_size=12, filter_k=None,
+                data_norm='mean', color_mean=None, color_std=None):
+    """One scene of test_s3dis.py:186-238 end to end on the device: coord [n,3] (scene coordinates), feat [n,3] (0..255 colours)
+    -> int32 labels [n].  data_load (voxel parts) -> data_process (covering crops, normalisation) -> batches of `batch_size`
+    crops through the eval-mode model -> softmax votes -> decision -> optional kNN(filter_k) label median filter."""
+    dev = next(model.parameters()).device
+    coord = coord.to(dev, dtype=torch.float32).contiguous()
+    feat = feat.to(dev, dtype=torch.float32).contiguous()
+    idx_data = scene_parts(coord, voxel_size)
+    idx_list, coord_list, feat_list, _ = data_process(coord, feat, idx_data, voxel_max, data_norm, color_mean, color_std)
+    return scene_inference(model, coord_list, feat_list, idx_list, coord.shape[0], num_class, batch_size=batch_size,
+                           filter_k=filter_k, coord_all=coord)

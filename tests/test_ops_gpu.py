@@ -80,7 +80,10 @@ def _packed(sizes, seed):
     return xyz, off
 
 
-@pytest.mark.parametrize("sizes,stride", [((1000, 500, 2047), 4), ((40960,), 16), ((10240, 10240, 300), 4), ((5, 9), 2)])
+@pytest.mark.parametrize("sizes,stride", [((1000, 500, 2047), 4), ((40960,), 16), ((10240, 10240, 300), 4), ((5, 9), 2),
+                                          # a segment beyond the register-resident capacity (16 CTAs x 512 threads x 16 points):
+                                          # the streaming plan with the caller's scratch buffer (whole-scene sizes)
+                                          ((150000, 3000), 250), ((131072 - 1024, 200), 128), ((131073, 1077), 512)])
 def test_fps_packed_matches_oracle(sizes, stride):
     xyz, off = _packed(sizes, 3)
     noff = torch.tensor(np.cumsum([s // stride for s in sizes]), dtype=torch.int32)

@@ -163,6 +163,38 @@ def test_scene_parts_and_crop_plan_match_restatement():
     assert bool(covered.all())                                              # every scene point receives at least one vote
 
 
+def test_infer_scene_end_to_end_covers_every_point():
+    """parts -> covering crops -> batched eval forward -> votes -> decision -> median filter, one call; every point is voted
+    for (no NaN row reaches the decision) and a seeded rerun reproduces the labels (up to vote-order ties)"""
+    from repsurf_b200.models import RepSurfSeg
+    from repsurf_b200.seg import scene as S
+    from oracle.model_ref import det_fill_
+    n = 90_000
+    xyz = (_room(n, 15) * torch.tensor([0.2, 0.2, 1.0])).contiguous()
+    feat = (torch.rand(n, 3, generator=torch.Generator().manual_seed(16)) * 255).contiguous()
+    model = det_fill_(RepSurfSeg()).to(cuda)
+    np.random.seed(2)
+    lab = S.infer_scene(model, xyz, feat, 13, voxel_size=0.04, voxel_max=24_000, batch_size=3, filter_k=32)
+    assert lab.shape == (n,) and lab.dtype == torch.int32 and int(lab.min()) >= 0 and int(lab.max()) < 13
+    np.random.seed(2)
+    votes_before = S.SceneVotes                                           # the vote counts of a second pass: all >= 1
+    counts = {}
+
+    class Probe(votes_before):
+        def decide(self):
+            counts["min"] = float(self.count.min())
+            return super().decide()
+    S.SceneVotes = Probe
+    try:
+        again = S.infer_scene(model, xyz, feat, 13, voxel_size=0.04, voxel_max=24_000, batch_size=3, filter_k=32)
+    finally:
+        S.SceneVotes = votes_before
+    assert counts["min"] >= 1.0
+    # votes of one batch are accumulated with float atomics: three or more crops of a batch that share a point may add up in a
+    # different order, so a class tie at the last ulp may fall the other way
+    assert float((again == lab).float().mean()) > 0.999
+
+
 @pytest.mark.parametrize("rows,nc,ignore", [(50_000, 13, None), (4097, 13, 255), (1000, 20, 3)])
 def test_cross_entropy_matches_torch(rows, nc, ignore):
     """seg/loss.CrossEntropyLoss (one kernel: value + gradient) against nn.CrossEntropyLoss in fp64, on the row-padded logits
