@@ -157,7 +157,7 @@ def test_scene_parts_and_crop_plan_match_restatement():
     for a, b in zip(gf, wf):
         assert np.array_equal(a.cpu().numpy(), (b).astype(np.float32))
     for a, b in zip(gc, wc):
-        assert np.abs(a.cpu().numpy() - b).max() < 1e-5                     # centring: fp64 mean here, fp32 in numpy
+        assert np.abs(a.cpu().numpy() - b).max() < 5e-5                     # centring: fp64 mean here, fp32 running sum in numpy
     covered = torch.zeros(n, dtype=torch.bool)
     covered[torch.cat([i.cpu() for i in gi])] = True
     assert bool(covered.all())                                              # every scene point receives at least one vote
