@@ -319,13 +319,29 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
         opt.step()
         return loss
 
-    # the dense classification step has static shapes and is host-bound when issued eagerly (~300 launches of a few us):
-    # forward + backward + SGD are captured once in a CUDA graph and replayed (repsurf_b200/graph.py).  One process only -
-    # the N>1 run keeps the eager step with its overlapped all-reduce.  RSB_CLS_EAGER=1 forces the eager step.
-    gstep = None
+    # Both steps have static shapes here (fixed B x N; fixed offsets) and are captured once in a CUDA graph and replayed
+    # (repsurf_b200/graph.py): issued eagerly the classification step is host-bound (~300 launches of a few us), and the
+    # segmentation step (~370 launches, 19.6 ms of GPU work) becomes host-bound on a box with a slow host (measured 25.3 ms).
+    # One process: forward + backward + SGD in the graph.  N > 1 (segmentation): forward + backward in the graph, then the
+    # gradient all-reduce and the optimizer step eagerly; classification keeps its eager step with the overlapped all-reduce.
+    # RSB_CLS_EAGER=1 / RSB_SEG_EAGER=1 force the eager step; a capture that fails falls back to it and says so (graph_error).
+    gstep, graph_error = None, None
     if workload == "cls" and world == 1 and not os.environ.get("RSB_CLS_EAGER"):
         from repsurf_b200.graph import GraphedTrainStep
         gstep = GraphedTrainStep(model, crit, opt, [devin[0]], devin[1])
+    elif workload == "seg" and not os.environ.get("RSB_SEG_EAGER"):
+        from repsurf_b200.graph import graphed_seg_step
+        try:
+            gstep = graphed_seg_step(model, crit, opt, devin[0], devin[1], devin[2], devin[3], optimizer_in_graph=(world == 1),
+                                     after_backward=(fg.allreduce_mean if world > 1 else None),
+                                     capture_error_mode="global" if world == 1 else "thread_local")
+        except Exception as e:                                # noqa: BLE001 - any capture failure: the eager step still runs
+            graph_error = f"{type(e).__name__}: {e}"[:300]
+            gstep = None
+            torch.cuda.synchronize()
+            opt.zero_grad(set_to_none=True)
+    if gstep is not None and workload == "seg":
+        h2d_bytes -= host[2].numel() * host[2].element_size()     # the offsets are fixed by the capture, not copied per step
 
     def step_eager():
         return fwd_bwd(devin)
@@ -337,12 +353,14 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
 
     def step_e2e():
         if gstep is not None:                                # pinned host -> the graph's static buffers -> replay -> loss read
-            return float(gstep([host[0]], host[1]))
+            if workload == "seg":
+                return float(gstep([host[0], host[1], gstep.static_in[2]], host[3]).detach())
+            return float(gstep([host[0]], host[1]).detach())
         inp = [t.to(dev, non_blocking=True) for t in host]
         if workload == "seg":
             PS.register_offsets(inp[2], host[2].tolist())   # the host already holds the offsets it uploads
         loss = fwd_bwd(inp)
-        return float(loss)                                   # D2H read of the step's result
+        return float(loss.detach())                          # D2H read of the step's result
 
     def barrier():
         if world > 1:
@@ -437,7 +455,7 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
     if full and workload == "seg":
         ctr = torch.zeros(3, dtype=torch.int64, device=dev)
         _native.lib().rsb_knn_grid_set_counters(ctr.data_ptr())
-        step_resident()
+        step_eager()                                         # eager: a graph replay carries the launch arguments of its capture
         torch.cuda.synchronize()
         _native.lib().rsb_knn_grid_set_counters(None)
         knn_work = [int(v) for v in ctr.tolist()]
@@ -448,7 +466,7 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches), "clocks": clk, "per_entry": per_entry, "knn_work": knn_work, "ms_serial": ms_serial,
            "host_issue_ms": {k: (v if isinstance(v, list) else round(v, 3)) for k, v in host_issue.items()},
-           "device_allocs": int(device_allocs), "cuda_graph": gstep is not None}
+           "device_allocs": int(device_allocs), "cuda_graph": gstep is not None, "graph_error": graph_error}
     del model, opt, fg, devin, gstep
     torch.cuda.empty_cache()
     return res
@@ -638,6 +656,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl["name"], "clouds_per_gpu": wl["clouds"], "points_per_cloud": wl["n"], "parallelism": f"dp{world}",
                    "optimizer_step": "SGD momentum inside the timed region", "tf32": False, "cuda_graph": r["cuda_graph"],
+                   "cuda_graph_error": r["graph_error"],
                    "l2": "per-step working set (activations > 126 MB) exceeds L2; no explicit flush"},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": roof, "rooflines": rooflines,
         "entry_time_share": entry_share, "dominant_entry": dom[0] if dom else None, "clocks": r["clocks"],

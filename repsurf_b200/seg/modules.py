@@ -271,10 +271,15 @@ class UmbrellaSurfaceConstructor(nn.Module):
             idx, _ = P.knnquery(self.k, center, center, offset, offset)
             if self.random_inv:
                 # same draw as the reference: numpy global RNG, one value per cloud (recons_utils.py:28-37)
-                keep = np.random.rand(offset.shape[0]) < 0.5
                 sizes = P._sizes(P.host_offsets(offset))
-                sign = torch.from_numpy(np.where(keep, 1.0, -1.0).astype(np.float32))
-                sign = sign.pin_memory().to(center.device, non_blocking=True)
+                if torch.cuda.is_current_stream_capturing():
+                    # a host draw (and the copy out of its temporary pinned buffer) would be frozen into the graph: draw on the
+                    # device, from torch's graph-aware generator, so that every replay flips afresh (same distribution)
+                    sign = (torch.rand(offset.shape[0], device=center.device) < 0.5).float() * 2. - 1.
+                else:
+                    keep = np.random.rand(offset.shape[0]) < 0.5
+                    sign = torch.from_numpy(np.where(keep, 1.0, -1.0).astype(np.float32))
+                    sign = sign.pin_memory().to(center.device, non_blocking=True)
                 flip = torch.repeat_interleave(sign, P.const_tensor(sizes, torch.int64, center.device),
                                                output_size=center.shape[0])
             else:
