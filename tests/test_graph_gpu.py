@@ -53,7 +53,8 @@ def test_graphed_train_step_matches_eager_loop():
         da, db = (a - ref).double(), (b - ref).double()
         if a.dim() > 1:
             assert float(da.norm()) > 0, n                  # every weight moved (a bias in front of a BatchNorm has no gradient)
-        assert float((da - db).norm()) <= 0.15 * float(da.norm()), (n, float((da - db).norm()), float(da.norm()))
+        floor = 2e-7 * (1.0 + float(ref.double().norm()))   # fp32 resolution of the parameter itself: updates below it are rounding
+        assert float((da - db).norm()) <= 0.15 * float(da.norm()) + floor, (n, float((da - db).norm()), float(da.norm()))
 
     start = {n: v.clone() for n, v in eager.state_dict().items()}
     for (n, a), b in zip(start.items(), graphed.state_dict().values()):
@@ -156,7 +157,8 @@ def test_graphed_seg_step_matches_eager_loop(opt_in_graph):
         da, db = (a - ref).double(), (b - ref).double()
         if a.dim() > 1:
             assert float(da.norm()) > 0, n                  # every weight moved (a bias in front of a BatchNorm has no gradient)
-        assert float((da - db).norm()) <= 0.15 * float(da.norm()), (n, float((da - db).norm()), float(da.norm()))
+        floor = 2e-7 * (1.0 + float(ref.double().norm()))   # fp32 resolution of the parameter itself: updates below it are rounding
+        assert float((da - db).norm()) <= 0.15 * float(da.norm()) + floor, (n, float((da - db).norm()), float(da.norm()))
 
     start = {n: v.clone() for n, v in eager.state_dict().items()}
     for (n, a), b in zip(start.items(), graphed.state_dict().values()):
