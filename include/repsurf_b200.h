@@ -273,6 +273,9 @@ typedef struct {
  * every stored tensor of the operands is 16-byte aligned with a row pitch that is a multiple of 4 floats, else the
  * first-generation cp.async kernels (csrc/mlp_tc.cu); 1 = always the first generation (A/B comparisons, tests). */
 void rsb_tc_set_generation(int gen);
+/* SM budget of the persistent row GEMMs that follow (0 = all SMs): for launches the caller knows to overlap a long-running
+ * cluster launch on another stream (the next level's FPS), so that no CTA has to wait for a second wave. */
+void rsb_tc_set_sm_budget(int sms);
 /* Y = A @ W^T with W pre-split by rsb_linear_tc_prep_weight(N, A->K, ...). */
 int rsb_gemm_rows(long rows, int N, const rsb_opnd_t *A, const float *Wp, const rsb_epi_t *E, cudaStream_t stream);
 /* dW[m, n] += sum_r G(r, m) * X(r, n);  dW is [G->K, ldw] fp32, accumulated with atomics (caller zeroes it). */

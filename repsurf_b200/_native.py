@@ -85,7 +85,7 @@ _SIGS = {
     "rsb_pool_bn_backward_dense": [_l, _i, _i, _p, _p, _p, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(_SIGS) + ["rsb_abi_version", "rsb_last_error", "rsb_launch_count", "rsb_reset_launch_count",
-                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation", "rsb_fps_set_generation", "rsb_knn_grid_set_counters", "rsb_sector_split_workspace_bytes"])
+                                "rsb_linear_tc_weight_floats", "rsb_knn_grid_workspace_bytes", "rsb_tc_set_generation", "rsb_tc_set_sm_budget", "rsb_fps_set_generation", "rsb_knn_grid_set_counters", "rsb_sector_split_workspace_bytes"])
 
 
 def build(force=False):
@@ -124,6 +124,8 @@ def lib():
         L.rsb_fps_set_generation.argtypes = [_i]
         L.rsb_tc_set_generation.restype = None
         L.rsb_tc_set_generation.argtypes = [_i]
+        L.rsb_tc_set_sm_budget.restype = None
+        L.rsb_tc_set_sm_budget.argtypes = [_i]
         _lib = L
     return _lib
 

@@ -1059,6 +1059,8 @@ int wgrad_narrow_launch(long rows, const rsb_opnd_t *G, const rsb_opnd_t *X, flo
 // RSB_WGRAD_TC=1: always the tensor-core weight-gradient kernel (A/B against the narrow-layer kernel)
 int g_wgrad_tc_only = [] { const char *v = getenv("RSB_WGRAD_TC"); return (v && v[0] && v[0] != '0') ? 1 : 0; }();
 int g_force_v1 = [] { const char *v = getenv("RSB_TC_V1"); return (v && v[0] && v[0] != '0') ? 1 : 0; }();
+// SM budget of the persistent row GEMMs (0 = all SMs), see rsb_tc_set_sm_budget
+int g_sm_budget = 0;
 
 bool opnd_tma_ok(const Opnd &O)
 {
@@ -1073,6 +1075,13 @@ bool opnd_tma_ok(const Opnd &O)
 }  // namespace
 
 RSB_EXPORT void rsb_tc_set_generation(int gen) { g_force_v1 = gen == 1 ? 1 : 0; }
+
+// The row GEMMs partition their tiles statically over one persistent CTA per SM.  When the caller KNOWS that a concurrent launch
+// on another stream holds some SMs for longer than the GEMM lasts (the cluster FPS of the next level, one CTA per SM for
+// milliseconds), the CTAs that find no SM run as a second wave after the first has finished: the launch takes twice as long.
+// With the grid limited to the SMs that are free it takes 148 / free instead.  Applies to the launches that follow, until reset
+// with 0; host-side state of the calling thread's launch sequence (not a device setting).
+RSB_EXPORT void rsb_tc_set_sm_budget(int sms) { g_sm_budget = sms > 0 ? sms : 0; }
 
 // Returns 0 when the launch was made, -1 when the problem is not eligible (the caller then uses the first-generation
 // kernel), > 0 on errors.
@@ -1161,7 +1170,9 @@ int rsb_gemm_rows2_launch(long rows, int N, const rsb_opnd_t *A, const float *Wp
         attr_set = true;
     }
     const long n_work = ((rows + TM - 1) / TM) * n_tiles * P.nsub;
-    const int grid = (int)(n_work < rsb_sm_count() ? n_work : rsb_sm_count());
+    int sms = rsb_sm_count();
+    if (g_sm_budget > 0 && g_sm_budget < sms) sms = g_sm_budget;
+    const int grid = (int)(n_work < sms ? n_work : sms);
     if (cfg2) gemm_rows2_kernel<8, 2><<<grid, RowsCfg<8, 2>::THREADS, smem, stream>>>(P);
     else gemm_rows2_kernel<16, 1><<<grid, RowsCfg<16, 1>::THREADS, smem, stream>>>(P);
     RSB_CHECK_LAUNCH("gemm_rows2_kernel");

@@ -12,6 +12,8 @@ Differences from the reference implementation (same results):
   * sectorized FPS runs fully on the device (pointops.sectorized_fps);
   * FPS emits the sampled coordinates; kNN emits sqrt distances; gathers use the grouping kernel.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -47,7 +49,20 @@ FUSE_GATHER = True
 # GeometryPlan runs sampling / neighbour search on side streams; False = everything in order on the caller's stream (per-kernel
 # timing without interference from concurrent kernels: bench.py's roofline pass)
 USE_SIDE_STREAMS = True
+# while the cluster FPS of the NEXT level holds SMs on the side stream, the forward GEMMs of a level launch one persistent CTA per
+# FREE SM instead of per SM (rsb_tc_set_sm_budget: no second wave behind the CTAs that found no SM).  RSB_SA_SM_BUDGET=0: off
+SM_BUDGET = os.environ.get("RSB_SA_SM_BUDGET", "1") != "0"
+# ... only for FPS launches of at least this many CTAs: a handful of single-CTA segments is over before the level's GEMMs start
+SM_BUDGET_MIN_CTAS = int(os.environ.get("RSB_SA_SM_BUDGET_MIN_CTAS", "16"))
 _SIDE_STREAMS = {}
+
+
+def _fps_ctas(sizes):
+    """SMs the packed FPS launch over clouds of these sizes occupies: one cluster per cloud, cluster size by the largest cloud's
+    padded position count (csrc/fps.cu fps_plan; every CTA of the kernel owns an SM)."""
+    n_max = -(-max(sizes) // 1024) * 1024
+    cs = 1 if n_max <= 8192 else 4 if n_max <= 16384 else 8 if n_max <= 65536 else 16
+    return cs * len(sizes)
 
 
 def _side_streams(device):
@@ -122,6 +137,14 @@ class GeometryPlan:
                     ev = torch.cuda.Event()
                     ev.record(s_knn)
                     self.knn[(fp_k, id(lv["new_center"]), id(lv["center"]))] = (idx, dist, ev, lv["new_center"], lv["center"])
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        for lv, nxt in zip(chain, chain[1:] + [None]):
+            # the FPS that runs on the side stream while this level's shared MLP runs on the main one is the NEXT level's
+            lv["sm_budget"] = 0
+            if USE_SIDE_STREAMS and nxt is not None and nxt["fps_idx"] is not None and not nxt["key"][2]:
+                ctas = _fps_ctas(P._sizes(P.host_offsets(nxt["offset"])))
+                if ctas >= SM_BUDGET_MIN_CTAS:
+                    lv["sm_budget"] = max(sms // 2, sms - ctas)
         for lv in chain:
             # side-stream allocations used by the main stream: tell the caching allocator
             for t in (lv["fps_idx"], lv["new_center"], lv["group_idx"]):
@@ -148,6 +171,11 @@ class GeometryPlan:
             return None
         torch.cuda.current_stream(center.device).wait_event(lv["ev"])
         return lv
+
+    def sm_budget(self, center):
+        """SMs left to the shared MLP of the level that starts at `center` (0 = all)."""
+        lv = self.sa.get(id(center))
+        return lv["sm_budget"] if (lv is not None and lv["center"] is center) else 0
 
     def neighbours(self, k, xyz, new_xyz):
         ent = self.knn.get((k, id(xyz), id(new_xyz)))
@@ -210,7 +238,15 @@ class SurfaceAbstractionCD(nn.Module):
         new_center, new_normal, rows, layout, new_offset = _sample_and_group(
             self.stride, self.nsample, center, normal, feature, offset, self.return_polar, self.num_sector,
             self.training)
-        return [new_center, new_normal, sa_mlp(rows, self.pos_channel, self, self.nsample, layout), new_offset]
+        budget = _ACTIVE_PLAN.sm_budget(center) if (_ACTIVE_PLAN is not None and SM_BUDGET) else 0
+        if budget:
+            N.lib().rsb_tc_set_sm_budget(budget)
+        try:
+            new_feature = sa_mlp(rows, self.pos_channel, self, self.nsample, layout)
+        finally:
+            if budget:
+                N.lib().rsb_tc_set_sm_budget(0)
+        return [new_center, new_normal, new_feature, new_offset]
 
 
 class SurfaceFeaturePropagationCD(nn.Module):
