@@ -58,6 +58,8 @@ def crop_plan(coord_part, voxel_max):
         crops.append(crop)
         if int(n_covered) >= n:
             return crops
+        if len(crops) > 2 * n:       # every seed's priority rises by 1 when it is used, so 2n seeds cover any finite cloud
+            raise RuntimeError("crop_plan does not converge (non-finite coordinates?)")
 
 
 def input_normalize(coord, feat, data_norm='mean', color_mean=None, color_std=None):
