@@ -22,15 +22,23 @@ def _worker(rank, world, port, q):
     torch.manual_seed(100 + rank)                      # different init per rank on purpose
     model = nn.Sequential(nn.Linear(6, 8), nn.ReLU(), nn.Linear(8, 3))
     broadcast_module(model)
-    fg = FlatGrads(model.parameters())
     g = torch.Generator().manual_seed(7)
     clouds = torch.randn(8, 16, 6, generator=g)         # 8 "clouds" globally, identical on every rank
     lo, hi = shard_range(8, rank, world)
+    # the arrangement of the graphed step with N > 1 (repsurf_b200/graph.py): the gradients were written by a graph replay, no
+    # hook ever ran and zero() was never called - allreduce_mean packs and reduces every run itself
+    plain_fg = FlatGrads(model.parameters())
+    model(clouds[lo:hi]).pow(2).mean().backward()
+    assert not plain_fg._hooked
+    plain = plain_fg.allreduce_mean().clone()
+    assert all(torch.equal(p.grad.flatten(), v) for p, v in zip(plain_fg.params, plain.split([p.numel() for p in plain_fg.params])))
+    fg = FlatGrads(model.parameters())
     fg.zero()
     model(clouds[lo:hi]).pow(2).mean().backward()
     flat = fg.allreduce_mean()
     assert all(torch.equal(p.grad.flatten(), v) for p, v in zip(fg.params, flat.split([p.numel() for p in fg.params])))
     first = flat.clone()
+    assert torch.allclose(first, plain, rtol=1e-6, atol=1e-8)      # hooks or not: the same mean
     # every run left while backward was still going (post-accumulate hooks), none had to be started by allreduce_mean
     assert fg._hooked and len(fg._members) == 2
     # gradient accumulation: a second backward after the runs have left is answered by one plain reduce of everything
