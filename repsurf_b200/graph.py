@@ -6,11 +6,11 @@ segmentation ~370 per step).  Issued eagerly the step is at the mercy of the hos
 issued launches half as fast as the others.  Every launch of this package goes to torch's current stream through the C-ABI
 and no entry point of either path synchronises or reads device memory on the host, so forward + backward (+ optimizer step)
 capture into one graph:
-  * dense classification (`classification/tool/train_cls_scanobjectnn.py:180-200` is the loop it stands for): B x N fixed;
-  * packed segmentation (`segmentation/tool/train.py:339-372`): the per-cloud sizes (offsets) must be the captured ones - the
+  * dense classification (`classification/tool/train_cls_scanobjectnn.py:212-234` is the loop it stands for): B x N fixed;
+  * packed segmentation (`segmentation/tool/train.py:280-290`): the per-cloud sizes (offsets) must be the captured ones - the
     host turns them into launch plans (sector quotas, FPS cluster plans, grid sizes) while capturing.  The reference's loader
-    crops every training cloud to `voxel_max` points, so full batches do have fixed offsets; a batch with other offsets needs
-    its own capture (or the eager step).  The geometry plan's side streams fork from and join the capturing stream, so the
+    crops every training cloud above `voxel_max` points to exactly `voxel_max` (`segmentation/util/data_util.py:46-48`), so
+    batches of large scenes do have fixed offsets; a batch with other offsets needs its own capture (or the eager step).  The geometry plan's side streams fork from and join the capturing stream, so the
     overlap of sampling / neighbour search with the GEMMs is part of the graph.
 With more than one process the gradient mean has to leave between backward and the optimizer: then forward + backward are
 the graph and `after_backward` (the all-reduce) and the optimizer step are issued eagerly after every replay.
