@@ -350,6 +350,13 @@ def run_ours(workload, args, rank, local_rank, world, dev, full):
             gstep = None
             torch.cuda.synchronize()
             opt.zero_grad(set_to_none=True)
+    if workload == "seg" and world > 1 and not os.environ.get("RSB_SEG_EAGER"):
+        # every rank must take the same path (the graphed step reduces the packed buffer once, the eager step in two runs from
+        # hooks): if the capture failed anywhere, everybody steps eagerly
+        ok = torch.tensor([1 if gstep is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0 and gstep is not None:
+            gstep, graph_error = None, "capture failed on another rank"
     if gstep is not None and workload == "seg":
         h2d_bytes -= host[2].numel() * host[2].element_size()     # the offsets are fixed by the capture, not copied per step
 
